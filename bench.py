@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Learner hot-path benchmark (BASELINE.json metric: learner transitions/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU learner
+
+A "step" is one pass of the learner hot path over one batch of synthetic trajectories: ring
+gather -> MLP actor-critic forward -> fused V-trace loss head -> backward -> (gradient
+all-reduce) -> fused Adam. Workload (BASELINE.json configs[3] / north_star target): batch 1024
+trajectories x T=100 transitions per GPU, 1024-byte records. `value` is timed with the
+trajectories already resident in HBM; `e2e` goes through the reference-facing API with host
+buffers: SharedBuffer.write (actor threads) -> Learner.trainModel -> loss read-back.
+Under torchrun every rank runs the same per-GPU batch (weak scaling) and the gradient arena is
+sum-all-reduced with NCCL; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "learner_transitions_per_s"
+UNIT = "transitions/s"
+REC_WORDS, Z_DIM, NUM_ACTIONS = 256, 162, 16
+W_MU, W_ACTION, W_REWARD, W_DISCOUNT, W_AUX = 162, 178, 179, 180, 181
+AC_FWD_FLOPS_PER_TRANSITION = 2.0 * (162 * 512 + 4 * 512 * 512 + 17 * 512)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU per step (M)")
+    ap.add_argument("--seq", type=int, default=100, help="transitions per trajectory (T = entry size S)")
+    ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--writers", type=int, default=8, help="actor threads feeding the ring in the e2e leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def synth_slots(seed: int, m: int, t: int) -> np.ndarray:
+    """Synthetic trajectories in the record layout of DESIGN.md: obs and
+    behaviour logits ~N(0,1), uniform actions, rewards ~N(0,1), done~Bernoulli(0.01) ->
+    discount 0.99(1-done), bootstrap ~N(0,1). Returns uint8 [m, t*1024]."""
+    rng = np.random.default_rng(seed)
+    w = np.zeros((m, t, REC_WORDS), np.float32)
+    w[:, :, :Z_DIM] = rng.standard_normal((m, t, Z_DIM), dtype=np.float32)
+    w[:, :, W_MU:W_MU + NUM_ACTIONS] = rng.standard_normal((m, t, NUM_ACTIONS), dtype=np.float32)
+    w[:, :, W_ACTION] = rng.integers(0, NUM_ACTIONS, size=(m, t)).astype(np.int32).view(np.float32)
+    w[:, :, W_REWARD] = rng.standard_normal((m, t), dtype=np.float32)
+    w[:, :, W_DISCOUNT] = (0.99 * (rng.random((m, t)) >= 0.01)).astype(np.float32)
+    w[:, t - 1, W_AUX] = rng.standard_normal(m, dtype=np.float32)
+    return w.reshape(m, t * REC_WORDS).view(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not f[0].isdigit() or int(f[0]) != self.device:
+                continue
+            if not any(a <= ts <= b for a, b in windows):
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_baseline_port(seq: int, budget_s: float):
+    """The oracle's float64 restatement of the SAME workload (V-trace actor-critic step) on the
+    host cores: a bounded sample of 8-trajectory steps. kind = "port"."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import pyoracle as po
+    o = po.Oracle()
+    rng = np.random.default_rng(0)
+    params = (rng.standard_normal(po.AC_PARAMS) * 0.04).astype(np.float32)
+    O = o.actor_critic(params, lr=5e-4)
+    m = 8
+    slots = synth_slots(99, m, seq)
+    dec = o.decode_vtrace(slots, m, seq)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.loss_grad(*dec)
+        O.opt_step()
+        n += 1
+        if time.perf_counter() - t0 >= budget_s or n >= 64:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n * m * seq / dt, "unit": UNIT, "cores": o.num_threads, "kind": "port",
+            "sample": f"{n} V-trace actor-critic steps of {m} x {seq} transitions (float64 C port, OpenMP), {dt:.1f} s"}
+
+
+def reference_libtorch(batch: int, seq: int, warmup: int, steps: int):
+    """The reference's own learner math: cmd/libtorch_bench train_step (FarmerLstm, MSE, Adam lr 5e-4)
+    compiled from the reference's sources into oracle/_ref, on the host cores."""
+    from oracle import pyoracle as po
+    if not os.path.exists(po.REF_NN_SO):
+        return None
+    r = po.RefNN(seed=1, opt="adam", lr=5e-4, loss="mse")
+    ms = r.bench(batch, seq, warmup, steps)
+    return {"ms_per_step": ms, "value": batch * seq / (ms / 1e3), "cores": r.num_threads}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU learner step on this box's host cores. The reference has
+    no V-trace: its learner math is libtorch_bench's FarmerLstm/MSE/Adam
+    train_step, timed here at the same batch x seq through oracle/_ref. If oracle/_ref is missing
+    the oracle's C port of the V-trace step is timed instead."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = {"workload": f"learner step, batch {args.batch} x T={args.seq} (reference arm: libtorch_bench FarmerLstm "
+                       f"MSE/Adam train_step on CPU; the reference has no V-trace)",
+           "batch_per_gpu": args.batch, "seq_len": args.seq}
+    ref = reference_libtorch(args.batch, args.seq, args.warmup, args.steps)
+    if ref is not None:
+        value, ms, kind, cores = ref["value"], ref["ms_per_step"], "reference", ref["cores"]
+        sample = f"{args.steps} train_step calls at batch {args.batch} x seq {args.seq} after {args.warmup} warm-ups"
+    else:
+        b = cpu_baseline_port(args.seq, max(args.cpu_seconds, 10.0))
+        value, kind, cores, sample = b["value"], "port", b["cores"], b["sample"]
+        ms = args.batch * args.seq / value * 1e3
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import freeimpala_b200 as fi
+    from freeimpala_b200._lib import FiBatch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:  # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), *sys.argv]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    M, T = args.batch, args.seq
+    slot_bytes = T * 1024
+    K, W = args.steps, max(args.warmup, 0)
+    cap = 2 * M
+    L = fi.Learner(1, cap, T, M, model="mlp_actor_critic", device=local, gemm_mode=args.gemm_mode, seed=1, lr=5e-4)
+    if world > 1:
+        ids = [fi.Learner.dp_create_ids(1) if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        L.dp_init(ids[0], rank, world)
+    lib = fi.load_library()
+    stream_ptr = lib.fi_learner_stream(L._h, 0)
+    ext = torch.cuda.ExternalStream(stream_ptr, device=torch.device("cuda", local))
+
+    # two distinct synthetic batches per rank, in pinned host memory and (for `value`) in an HBM ring
+    host_ptr = lib.fi_host_alloc(cap * slot_bytes)
+    host = np.ctypeslib.as_array((C.c_uint8 * (cap * slot_bytes)).from_address(host_ptr)).reshape(cap, slot_bytes)
+    host[:M] = synth_slots(1000 + rank, M, T)
+    host[M:] = synth_slots(2000 + rank, M, T)
+    ring_dev = torch.empty((cap, slot_bytes), dtype=torch.uint8, device="cuda")
+    ring_dev.copy_(torch.from_numpy(host))
+    batch_dev = torch.empty((M, slot_bytes), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def device_step(i: int):
+        first = (i * M + M // 2) % cap  # every other step wraps around the ring end
+        fi.ops.gather(ring_dev.data_ptr(), cap, slot_bytes, first, M, batch_dev.data_ptr(), stream_ptr)
+        raw = FiBatch(batch_dev.data_ptr(), M, slot_bytes, stream_ptr, 0)
+        L.trainModel(0, fi.Batch(raw))
+
+    sampler = ClockSampler(local)
+    windows = []
+    if rank == 0:
+        sampler.start()
+
+    # ---------------- value: inputs resident in HBM -------------------------------------------
+    for i in range(max(W, 3)):
+        device_step(i)
+    L.sync(0)
+    barrier()
+    torch.cuda.synchronize()
+    fi.prof_collect()
+    fi.prof_enable(True)
+    n0 = fi.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    ev0.record(ext)
+    for i in range(K):
+        device_step(i)
+    ev1.record(ext)
+    L.sync(0)
+    torch.cuda.synchronize()
+    barrier()
+    w1 = time.perf_counter()
+    windows.append((w0, w1))
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = fi.kernel_launch_count() - n0
+    fi.prof_enable(False)
+    prof = fi.prof_collect()
+    losses = L.last_losses(0)
+    ms_per_step = ms_total / K
+    value = world * M * T / (ms_per_step / 1e3)
+
+    # ---------------- e2e: host buffers through SharedBuffer.write -> trainModel -> loss read-back ---
+    e2e = None
+    if not args.no_e2e:
+        ring = L.getSharedBuffers()[0]
+        nw = max(1, args.writers)
+
+        def writer(j: int, steps: int):
+            for s in range(steps):
+                base = (s % 2) * M
+                for i in range(j, M, nw):
+                    ring.write(host[base + i])
+
+        def e2e_steps(steps: int):
+            ts = [threading.Thread(target=writer, args=(j, steps)) for j in range(nw)]
+            for t in ts:
+                t.start()
+            for _ in range(steps):
+                b = ring.readBatch(M, stream_ptr)
+                L.trainModel(0, b)
+                L.last_losses(0)  # device -> host read of the step's result
+            for t in ts:
+                t.join()
+
+        e2e_steps(max(W, 3))
+        L.sync(0)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_steps(K)
+        L.sync(0)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        windows.append((t0, t1))
+        e2e_s = max_over_ranks(t1 - t0)
+        e2e = {"value": world * M * T * K / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / K * 1e3,
+               "h2d_bytes_per_step": world * M * slot_bytes,
+               "d2h_bytes_per_step": world * (32 + 4 * L.param_count),
+               "path": f"SharedBuffer.write x{M} from {nw} actor threads (pinned slot + cudaMemcpyAsync on the side "
+                       f"stream) -> readBatch (gather kernel) -> Learner.trainModel -> losses D2H; weights published D2H"}
+
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    # ---------------- per-kernel roofline from the timed region --------------------------------------
+    peaks = measured_peaks()
+    kernels = {}
+    for name, r in prof.items():
+        if r["launches"] == 0 or r["total_ms"] <= 0:
+            continue
+        avg_ms = r["total_ms"] / r["launches"]
+        per_launch = r["work"] / r["launches"]
+        if r["unit"] == "bytes":
+            ach = per_launch / (avg_ms / 1e3) / 1e9
+            peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
+        else:
+            ach = per_launch / (avg_ms / 1e3) / 1e12
+            peak, unit, bound = peaks["bf16_tflops_sustained"], "TFLOP/s", "tensor"
+        kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                         "launches_per_step": r["launches"] / K, "avg_us": avg_ms * 1e3,
+                         "share_of_step": r["total_ms"] / (ms_per_step * K) if world == 1 else None}
+    dominant = max(kernels, key=lambda k: prof[k]["total_ms"]) if kernels else None
+    roofline = None
+    if dominant:
+        d = kernels[dominant]
+        roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": None, "peak_source": peaks["source"],
+                    "note": "tensor peak = cuBLAS bf16 sustained; this kernel computes fp32-accurate products "
+                            "(3xTF32 on tcgen05 or fp32 FFMA), whose ceiling is <= 1/6 of the bf16 peak"
+                            if d["bound"] == "tensor" else "HBM copy peak"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_port(T, args.cpu_seconds)
+        try:
+            ref = reference_libtorch(64, T, 2, 5)
+            if ref:
+                cpu["reference_libtorch_farmer_b64"] = {"value": ref["value"], "unit": UNIT, "cores": ref["cores"],
+                                                        "ms_per_step": ref["ms_per_step"],
+                                                        "sample": "libtorch_bench train_step, batch 64 x seq 100 (README shape)"}
+        except Exception as e:  # the reference build is optional on the GPU box
+            cpu["reference_libtorch_farmer_b64"] = {"unavailable": str(e)[:200]}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"vtrace_mlp_actor_critic learner step, batch {M} x T={T} per GPU "
+                                      f"(BASELINE.json configs[3]; records of 1024 B)",
+                          "batch_per_gpu": M, "global_batch": M * world, "seq_len": T, "params": L.param_count,
+                          "optimizer": "adam lr 5e-4", "gemm_mode": args.gemm_mode,
+                          "parallelism": f"dp{world} (batch sharded, NCCL sum-allreduce of the flat gradient arena)",
+                          "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
+                          "flops_per_step": 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
+               "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+               "cpu_baseline": cpu, "losses_last_step": [float(x) for x in losses]}
+        print(json.dumps(out), flush=True)
+    L.close()
+    lib.fi_host_free(host_ptr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)

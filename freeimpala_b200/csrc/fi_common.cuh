@@ -7,7 +7,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/fi_learner.h"
 
@@ -67,6 +69,64 @@ inline int check_launch(const char* what) {
     return FI_OK;
 }
 
+// ---- per-kernel device timing (fi_prof_enable / fi_prof_collect) --------------------------
+// When enabled, every launch is bracketed by two CUDA events on the launching stream and tagged
+// with its algorithmic work (bytes or flops), so bench.py can report achieved GB/s / TFLOP/s per
+// kernel from the same timed region the headline number comes from. Disabled: one relaxed load.
+enum WorkUnit { kWorkBytes = 0, kWorkFlops = 1 };
+struct ProfRec {
+    const char* name;
+    double work;
+    int unit;
+    cudaEvent_t a, b;
+};
+struct ProfState {
+    std::atomic<bool> on{false};
+    std::mutex mu;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+};
+inline ProfState& prof() {
+    static ProfState s;
+    return s;
+}
+class LaunchScope {
+public:
+    LaunchScope(const char* name, cudaStream_t st, double work, int unit) : name_(name), st_(st) {
+        ProfState& p = prof();
+        if (!p.on.load(std::memory_order_relaxed)) return;
+        std::lock_guard<std::mutex> g(p.mu);
+        while (p.pool.size() < p.used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            p.pool.push_back(e);
+        }
+        rec_.name = name;
+        rec_.work = work;
+        rec_.unit = unit;
+        rec_.a = p.pool[p.used++];
+        rec_.b = p.pool[p.used++];
+        active_ = cudaEventRecord(rec_.a, st) == cudaSuccess;
+    }
+    int done() {  // call right after the <<<>>> launch
+        const int rc = check_launch(name_);
+        if (active_) {
+            cudaEventRecord(rec_.b, st_);
+            ProfState& p = prof();
+            std::lock_guard<std::mutex> g(p.mu);
+            p.recs.push_back(rec_);
+        }
+        return rc;
+    }
+
+private:
+    const char* name_;
+    cudaStream_t st_;
+    ProfRec rec_{};
+    bool active_ = false;
+};
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -83,5 +143,32 @@ constexpr int kWDiscount = 180;
 constexpr int kWAux = 181;
 constexpr int kWX = 192;
 constexpr int kXPerRec = 64;
+constexpr int kHid = 512;                    // trunk width (reference main.cpp:17-21)
+constexpr int kHead = kNumActions + 1;       // fused policy/value head rows
+constexpr int kLstmH = 128;                  // reference main.cpp:16
+
+#ifdef __CUDACC__
+// ---- streaming 16-byte global accesses (no L1 allocation: every byte is touched once) ------
+__device__ __forceinline__ int4 ld_stream16(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream16(int4* p, const int4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
 
 }  // namespace fi

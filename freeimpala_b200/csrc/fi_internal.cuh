@@ -1,0 +1,33 @@
+// Internal (non-ABI) entry points shared between the translation units of the library.
+#pragma once
+#include "fi_common.cuh"
+
+namespace fi {
+
+int launch_gather(const void* ring_base, size_t capacity, size_t slot_bytes, size_t first, size_t m, void* dst,
+                  cudaStream_t stream);
+int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v,
+               float grad_scale, cudaStream_t stream);
+int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount, const float* reward,
+                       const float* value, const float* bootstrap, float rho_bar, float c_bar, float pg_rho_bar,
+                       float lambda_, float* vs, float* pg_adv, cudaStream_t stream);
+int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar, float c_bar,
+                            float pg_rho_bar, float lambda_, float baseline_cost, float entropy_cost, float* dhead,
+                            float* vs, float* pg_adv, double* losses, cudaStream_t stream);
+
+// trans: 0 "NT" C = A[m,k] B[n,k]^T; 1 "NN" C = A[m,k] B[k,n]; 2 "TN" C = A[k,m]^T B[k,n].
+int launch_gemm_simt(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c,
+                     int ldc, const float* bias, int relu, const float* mask, int ldmask, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_simt_workspace_bytes(int trans, int m, int n, int k);
+int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+size_t colsum_workspace_bytes(int m, int n);
+
+// Dispatching GEMM (gemm.cu): picks the tcgen05 3xTF32 kernel or the SIMT kernel per fi_gemm_mode.
+int launch_gemm(int mode, int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c,
+                int ldc, const float* bias, int relu, const float* mask, int ldmask, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_workspace_bytes(int mode, int trans, int m, int n, int k);
+
+}  // namespace fi

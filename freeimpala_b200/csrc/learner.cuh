@@ -1,0 +1,115 @@
+// Internal learner structures shared by learner.cu (host orchestration, model store, DP),
+// model_ac.cu (MLP actor-critic V-trace step) and model_farmer.cu (FarmerLstm step).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "fi_internal.cuh"
+
+namespace fi {
+
+struct TensorSpec {
+    size_t offset, numel, rows, cols;
+    int fan_in;
+};
+
+// Versioned weight publication: replaces Model / ModelManager::{getModel,updateModel,
+// getLatestVersion,waitForModelUpdate} (reference data_structures.h:43-157, 433-480).
+// After each optimiser update the learner stream snapshots the parameter arena into one of two
+// HBM snapshots (D2D, ~1.5 us); the publication stream copies that snapshot into one of three
+// pinned host blobs and a host callback flips `published` (the reference's shared_ptr swap,
+// :441-451). Actors read the published blob under a shared lock: many readers, no copy under
+// an exclusive mutex (the reference's getData() copies 1 MiB under model_mutex, :135-138).
+struct ModelStore {
+    size_t bytes = 0;                       // blob size = param_count * 4
+    float* dev_snap[2] = {nullptr, nullptr};
+    cudaEvent_t snap_ready[2] = {nullptr, nullptr};  // D2D into the snapshot finished (learner stream)
+    cudaEvent_t snap_free[2] = {nullptr, nullptr};   // D2H out of the snapshot finished (pub stream)
+    cudaEvent_t infer_done[2] = {nullptr, nullptr};  // last inference reading the snapshot finished
+    bool snap_free_recorded[2] = {false, false}, infer_recorded[2] = {false, false};
+    unsigned char* host_buf[3] = {nullptr, nullptr, nullptr};
+    uint64_t buf_version[3] = {0, 0, 0};
+    int published = 0;                      // index into host_buf, guarded by rw
+    std::shared_mutex rw;                   // readers: shared; flip: exclusive
+    std::atomic<uint64_t> latest_version{0};
+    std::mutex mu;                          // snapshot / host-buffer rotation bookkeeping
+    std::mutex cv_mu;                       // waitForModelUpdate (:454-472)
+    std::condition_variable cv;
+    cudaStream_t pub_stream = nullptr;
+    int next_host = 1, next_snap = 1;
+    int newest_snap = 0;                    // snapshot holding the newest weights (inference)
+};
+
+struct PublishTicket {                      // argument of the publication host callback
+    ModelStore* store;
+    int host_index;
+    uint64_t version;
+};
+
+struct Player {
+    int index = 0;
+    std::mutex step_mu;         // serialises enqueueing on `stream` against checkpoint / arena access
+    cudaStream_t stream = nullptr;
+    float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    int64_t opt_step = 0;
+    uint64_t steps_done = 0;
+    uint64_t version = 1;       // version of the weights in `params` (Model ctor -> 1, :55-58,127)
+    double* d_losses = nullptr; // device double[4]
+    double* h_losses = nullptr; // pinned double[4]
+    cudaEvent_t losses_ready = nullptr, batch_ready = nullptr;
+    size_t last_rows = 0;
+    bool grads_valid = false;
+    // step workspaces (model specific, sized for batch_size x entry_size rows)
+    std::vector<float*> act;    // activations
+    float *d_a = nullptr, *d_b = nullptr, *head = nullptr, *dhead = nullptr;
+    void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;
+    void* colsum_ws = nullptr; size_t colsum_ws_bytes = 0;
+    void* model_ws = nullptr;   // model-private extra workspace (farmer LSTM)
+    unsigned char* stage_dev = nullptr;  // staged batch (fi_learner_stage_batch)
+    unsigned char* stage_host = nullptr; // pinned bounce buffer for pageable sources
+    size_t stage_bytes = 0;
+    // inference
+    std::mutex infer_mu;
+    cudaStream_t infer_stream = nullptr;
+    float *inf_in = nullptr, *inf_x = nullptr, *inf_out = nullptr;
+    float *inf_host_in = nullptr, *inf_host_x = nullptr, *inf_host_out = nullptr;  // pinned
+    std::vector<float*> inf_act;
+    void* inf_model_ws = nullptr;
+    size_t inf_rows_cap = 0, inf_t_cap = 0;
+    ModelStore store;
+    uint64_t checkpoint_counter = 0;
+    void* nccl_comm = nullptr;  // one communicator per player: players step concurrently
+};
+
+}  // namespace fi
+
+struct fi_learner {
+    fi_learner_config cfg;
+    std::string ckpt_dir;
+    std::vector<fi::TensorSpec> tensors;
+    size_t param_count = 0, arena_elems = 0;
+    std::vector<fi_ring*> rings;
+    std::vector<fi::Player*> players;
+    int dp_rank = 0, dp_world = 1;
+};
+
+namespace fi {
+// model_ac.cu
+int ac_alloc(fi_learner* l, Player* p);
+void ac_free(Player* p);
+int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int global_m);
+int ac_infer_alloc(fi_learner* l, Player* p, size_t rows);
+int ac_infer(fi_learner* l, Player* p, const float* params, const float* obs_dev, size_t rows, float* out_dev,
+             cudaStream_t stream);
+// model_farmer.cu
+int farmer_alloc(fi_learner* l, Player* p);
+void farmer_free(Player* p);
+int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int global_m);
+int farmer_infer_alloc(fi_learner* l, Player* p, size_t rows, size_t t);
+int farmer_infer(fi_learner* l, Player* p, const float* params, const float* z_dev, const float* x_dev, size_t rows,
+                 size_t t, float* out_dev, cudaStream_t stream);
+}  // namespace fi

@@ -44,6 +44,20 @@ FI_API const char* fi_version(void);
 /* Number of CUDA kernels this library has launched in this process (all streams). */
 FI_API uint64_t fi_kernel_launch_count(void);
 
+/* Per-kernel device timing. While enabled, every kernel launch of the library is bracketed by
+ * CUDA events on its launching stream and tagged with its algorithmic work. fi_prof_collect
+ * waits for the recorded launches, aggregates them by kernel name into out[0..max) and returns
+ * the number of distinct kernels; the window is then reset. */
+typedef struct fi_prof_entry {
+    char name[48];
+    uint64_t launches;
+    double total_ms;   /* sum of device durations */
+    double work;       /* sum of algorithmic bytes (unit 0) or flops (unit 1) */
+    int unit;
+} fi_prof_entry;
+FI_API void fi_prof_enable(int on);
+FI_API int fi_prof_collect(fi_prof_entry* out, int max_entries);
+
 /* ============================ trajectory ring ============================================
  * Replaces SharedBuffer (include/freeimpala/data_structures.h:191-307). One ring per
  * player. Host side: a bounded MPMC FIFO of `capacity` pinned-host slots of slot_bytes =
@@ -164,6 +178,10 @@ FI_API int fi_learner_stage_batch(fi_learner* l, int player, const void* host, s
 /* Results of the last step (synchronises the player's stream). losses[4]:
  * MSE-family: {loss,0,0,0}; V-trace: {total, pg, baseline, entropy}. */
 FI_API int fi_learner_last_losses(fi_learner* l, int player, float losses[4]);
+/* Same numbers in the double precision they are accumulated in (synchronises the stream). */
+FI_API int fi_learner_last_losses_f64(fi_learner* l, int player, double losses[4]);
+/* Wait until everything enqueued for this player (step and weight publication) has finished. */
+FI_API int fi_learner_sync(fi_learner* l, int player);
 FI_API uint64_t fi_learner_steps_done(fi_learner* l, int player);
 
 /* Flat fp32 parameter arena, in the reference's model.parameters() order (farmer: 16
@@ -175,6 +193,8 @@ FI_API int fi_learner_set_params(fi_learner* l, int player, const float* host, s
 FI_API int fi_learner_get_params(fi_learner* l, int player, float* host, size_t n);
 FI_API int fi_learner_get_grads(fi_learner* l, int player, float* host, size_t n);
 FI_API int fi_learner_set_grads(fi_learner* l, int player, const float* host, size_t n);
+/* Adam moments and step count (checkpoint-with-optimiser-state tests); m / v may be NULL. */
+FI_API int fi_learner_get_opt_state(fi_learner* l, int player, float* m, float* v, size_t n, int64_t* step);
 /* Device pointers into the arenas (for hosts that run their own collective on them). */
 FI_API void* fi_learner_grad_ptr(fi_learner* l, int player);
 FI_API void* fi_learner_param_ptr(fi_learner* l, int player);
@@ -200,13 +220,20 @@ FI_API int fi_model_load(fi_learner* l, const char* dir);
 
 /* ---- data parallelism across the GPUs of one box ---- */
 #define FI_DP_ID_BYTES 128
-/* Rank 0 creates the id; the host transports it to the other ranks (MPI_Bcast in the
- * reference's MPI mains, torch.distributed in bench.py); every rank then joins. After this,
- * fi_learner_step sum-allreduces the flat gradient arena (NCCL over NVLink/NVSwitch) between
- * backward and the optimiser update, and mean losses divide by the global batch. */
+/* Rank 0 creates one id per player (players step concurrently, so each owns a communicator);
+ * the host transports them to the other ranks (MPI_Bcast in the reference's MPI mains,
+ * torch.distributed in bench.py); every rank then joins. After this, fi_learner_step
+ * sum-allreduces the flat gradient arena (NCCL over NVLink/NVSwitch) between backward and the
+ * optimiser update, and mean losses divide by the global batch. NCCL is bound with dlopen
+ * (FI_NCCL_LIB overrides the library name); FI_ERR_NCCL if it cannot be found. */
 FI_API int fi_dp_create_id(void* id_out /* FI_DP_ID_BYTES */);
-FI_API int fi_learner_dp_init(fi_learner* l, const void* id, int rank, int world_size);
+FI_API int fi_learner_dp_init(fi_learner* l, const void* ids /* num_players * FI_DP_ID_BYTES */, int rank, int world_size);
 FI_API int fi_learner_dp_world(const fi_learner* l);
+
+/* Pinned (page-locked, portable) host memory for callers that stage their own batches: a
+ * pinned source lets fi_learner_stage_batch DMA straight from the caller's buffer. */
+FI_API void* fi_host_alloc(size_t bytes);
+FI_API void fi_host_free(void* p);
 
 /* ============================ operator layer =============================================
  * Stream-ordered launches of the individual sm_100a kernels on caller-owned DEVICE
@@ -220,10 +247,11 @@ FI_API int fi_op_gather(const void* ring_base, size_t capacity, size_t slot_byte
  * 24 B/transition of algorithmic traffic (+4 B/trajectory). */
 FI_API int fi_op_vtrace(int m, int t, const float* log_rho, const float* discount, const float* reward, const float* value, const float* bootstrap, float rho_bar, float c_bar, float pg_rho_bar, float lambda_, float* vs, float* pg_adv, void* stream);
 
-/* Fused V-trace loss head on a gathered batch: reads head[m*t, 17] (16 logits + value) and
- * the records' mu-logits/action/reward/discount/bootstrap; writes dhead[m*t,17] and
- * accumulates losses[4] = {total,pg,baseline,entropy} (must be zeroed by the caller). */
-FI_API int fi_op_vtrace_loss_head(const void* batch, int m, int t, const float* head, float rho_bar, float c_bar, float pg_rho_bar, float lambda_, float baseline_cost, float entropy_cost, float* dhead, float* vs, float* pg_adv, float* losses, void* stream);
+/* Fused V-trace loss head on a gathered batch [m, t records]: reads head[m*t, ldh] (16 policy
+ * logits + value per row, ldh >= 17) and the records' behaviour logits / action / reward /
+ * discount / bootstrap; writes dhead (same layout), optionally vs / pg_adv [m*t], and ADDS
+ * {total, pg, baseline, entropy} into losses[4] (double, zeroed by the caller). */
+FI_API int fi_op_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar, float c_bar, float pg_rho_bar, float lambda_, float baseline_cost, float entropy_cost, float* dhead, float* vs, float* pg_adv, double* losses, void* stream);
 
 /* One fused optimiser update over n contiguous fp32 values (28 B/param for Adam).
  * step counts from 1; grad_scale multiplies g first (1/world for averaged gradients). */
@@ -231,6 +259,7 @@ FI_API int fi_op_adam(int opt_kind, double lr, int64_t step, size_t n, float* p,
 
 /* C[m,n] = op(A) op(B) (+bias, ReLU). trans: 0 = "NT" A[m,k] B[n,k]; 1 = "NN" A[m,k] B[k,n];
  * 2 = "TN" A[k,m] B[k,n]. mode: fi_gemm_mode. fp32 in/out, fp32-accurate accumulation. */
+FI_API size_t fi_op_gemm_workspace_bytes(int trans, int m, int n, int k, int mode);
 FI_API int fi_op_gemm(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc, const float* bias, int relu, int mode, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -125,6 +125,8 @@ void orc_ac_get_params(const orc_ac* f, double* out);
 void orc_ac_get_grads(const orc_ac* f, double* out);
 void orc_ac_set_grads(orc_ac* f, const double* in);
 
+int orc_num_threads(void);
+
 #ifdef __cplusplus
 }
 #endif

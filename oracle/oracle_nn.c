@@ -485,3 +485,11 @@ void orc_ac_loss_grad(orc_ac* f, const float* obs, const float* mu_logits, const
     free(in0); free(head); free(logits); free(value); free(dlogits); free(dvalue); free(da); free(db_);
     for (int l = 0; l < 5; l++) free(act[l]);
 }
+
+/* Threads the OpenMP loops above use (bench.py reports it as cpu_baseline.cores). */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_num_threads(void) { return omp_get_max_threads(); }
+#else
+int orc_num_threads(void) { return 1; }
+#endif

@@ -101,6 +101,10 @@ class Oracle:
         L.orc_ac_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_ac_opt_step.argtypes = [C.c_void_p]
 
+    @property
+    def num_threads(self) -> int:
+        return self.lib.orc_num_threads()
+
     # ---- ring ----
     def ring(self, entry_size: int, capacity: int) -> "OracleRing":
         return OracleRing(self, entry_size, capacity)

@@ -23,5 +23,8 @@ def oracle():
 @pytest.fixture(scope="session")
 def fi():
     """The product C-ABI library through ctypes. GPU tests fail loudly if it is missing."""
+    from freeimpala_b200 import build
+    build.build()          # no-op when the in-tree .so is up to date
     import freeimpala_b200 as m
+    m.load_library()
     return m

@@ -1,0 +1,170 @@
+"""Learner-step parity through the C ABI (fi_learner_*) against the CPU oracle. Needs a B200.
+
+Tolerance (BASELINE.json north_star): loss and parameter relative error <= 1e-5 after N steps.
+The actor-critic V-trace step has no counterpart in the reference (parity vs the reference is
+unpinned); its checker is the float64 oracle. The FarmerLstm step is
+checked against the golden fixtures produced by the reference's own libtorch train_step.
+"""
+import os
+import tempfile
+import threading
+
+import numpy as np
+import pytest
+
+import _util as U
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _ac_learner(fi, m, t, **kw):
+    return fi.Learner(1, max(m, 2), t, m, 0, 0, kw.pop("ckpt", ""), "", 0, model="mlp_actor_critic", **kw)
+
+
+@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("m,t,steps", [(4, 7, 3), (64, 100, 3), (9, 33, 2)])
+def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
+    params = U.ac_params(11)
+    L = _ac_learner(fi, m, t, gemm_mode=gemm_mode, entropy_cost=0.01, baseline_cost=0.5)
+    assert L.param_count == po.AC_PARAMS
+    L.set_params(0, params)
+    O = oracle.actor_critic(params, lr=5e-4)
+    for s in range(steps):
+        obs, mu, act, rew, disc, boot = U.vtrace_batch(100 + s, m, t, done_p=0.03)
+        slots = po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)
+        want = O.loss_grad(obs, mu, act, rew, disc, boot)
+        batch = L.stage_batch(0, slots)
+        L.forward_backward(0, batch)
+        got = L.last_losses(0)
+        np.testing.assert_allclose(got, want, rtol=TOL, atol=1e-6 * abs(want[0]))
+        assert U.rel_l2(L.get_grads(0), O.grads()) < TOL
+        L.apply_update(0)
+        O.opt_step()
+        assert U.rel_l2(L.get_params(0), O.params()) < TOL
+    assert L.steps_done(0) == steps
+    L.close()
+
+
+def test_step_through_ring_equals_staged_step(fi, oracle):
+    """Ring write -> H2D on the side stream -> gather kernel -> step gives the same bits as the staged
+    batch: the ring path moves bytes only."""
+    m, t = 8, 12
+    params = U.ac_params(3)
+    obs, mu, act, rew, disc, boot = U.vtrace_batch(9, m, t)
+    slots = po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)
+    A = fi.Learner(1, 11, t, m, model="mlp_actor_critic", gemm_mode="simt")
+    B = fi.Learner(1, 11, t, m, model="mlp_actor_critic", gemm_mode="simt")
+    A.set_params(0, params)
+    B.set_params(0, params)
+    ring = A.getSharedBuffers()[0]
+    for i in range(9):  # advance the ring so that the batch wraps around
+        ring.write(np.full(t * 1024, i, np.uint8))
+    ring.readBatch(9)
+    for i in range(m):
+        assert ring.write(slots[i])
+    batch = ring.readBatch(m)
+    assert np.array_equal(batch.to_host(), slots)
+    A.trainModel(0, batch)
+    B.trainModel(0, B.stage_batch(0, slots))
+    assert np.array_equal(A.get_params(0), B.get_params(0))
+    A.close()
+    B.close()
+
+
+def test_model_store_versions_and_checkpoint(fi, oracle):
+    m, t = 4, 5
+    with tempfile.TemporaryDirectory() as d:
+        L = _ac_learner(fi, m, t, ckpt=d, gemm_mode="simt")
+        mm = L.getModelManager()
+        assert mm.getLatestVersion(0) == 1              # Model ctor -> version 1 (data_structures.h:52-58)
+        assert mm.getLatestVersion(5) == 0 and mm.getModel(5) is None
+        assert not mm.waitForModelUpdate(0, 1, 20)      # times out: nothing newer than 1
+        model = mm.getModel(0)
+        assert model.getVersion() == 1 and np.array_equal(model.as_float32(), L.get_params(0))
+        slots = po.pack_vtrace_slots(*U.vtrace_batch(1, m, t))
+        for s in range(3):
+            L.trainModel(0, L.stage_batch(0, slots))
+        assert mm.waitForModelUpdate(0, 3, 5000)
+        L.sync(0)
+        model = mm.getModel(0)
+        assert model.getVersion() == mm.getLatestVersion(0) == 4   # +1 per step (learner.h:40-45)
+        assert np.array_equal(model.as_float32(), L.get_params(0))
+        # checkpoint: little-endian u64 version + raw bytes, two files (data_structures.h:105-110,399-419)
+        mm.saveModel(0, 7)
+        raw = np.fromfile(os.path.join(d, "model_0_7.bin"), np.uint8)
+        assert raw.size == 8 + 4 * L.param_count and int(raw[:8].view("<u8")[0]) == 4
+        assert np.array_equal(raw[8:].view(np.float32), L.get_params(0))
+        assert np.array_equal(raw, np.fromfile(os.path.join(d, "model_0_latest.bin"), np.uint8))
+        mm.saveModel(0, 0)                              # iteration 0 -> per-player counter (:405)
+        assert os.path.exists(os.path.join(d, "model_0_0.bin"))
+        # resume with optimiser state: the continued run equals the uninterrupted one bit for bit
+        mm.saveModel(0, 9, with_optimizer_state=True)
+        L.trainModel(0, L.stage_batch(0, slots))
+        want = L.get_params(0)
+        os.remove(os.path.join(d, "model_0_latest.bin"))
+        R = _ac_learner(fi, m, t, gemm_mode="simt", seed=99)
+        assert R.getModelManager().loadModels(d) == 1   # highest-numbered file (model_0_9.bin)
+        assert R.getModelManager().getLatestVersion(0) == 4
+        assert R.get_opt_state(0)[2] == 3
+        R.trainModel(0, R.stage_batch(0, slots))
+        assert np.array_equal(R.get_params(0), want)
+        R.close()
+        L.close()
+
+
+def test_worker_threads_with_concurrent_actors(fi):
+    """configs[2] in miniature: p=2 players, actors writing from many threads, one worker thread per
+    player (learner.h:72-97), total_iterations honoured, versions advance by one per update."""
+    p, B, S, M, T = 2, 8, 6, 4, 5
+    L = fi.Learner(p, B, S, M, 0, 0, "", "", T, model="mlp_actor_critic", gemm_mode="simt")
+    bufs = L.getSharedBuffers()
+    L.start()
+
+    def actor(a):
+        rng = np.random.default_rng(a)
+        for i in range(T * M // 4):
+            for pl in range(p):
+                obs, mu, act, rew, disc, boot = U.vtrace_batch(int(rng.integers(1 << 30)), 1, S)
+                assert bufs[pl].write(po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)[0])
+
+    ts = [threading.Thread(target=actor, args=(a,)) for a in range(4)]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join(timeout=120)
+    for w in list(L.worker_threads):
+        w.join(timeout=120)
+    L.stop()
+    assert not L.errors
+    assert L.iterations_done == [T, T]
+    mm = L.getModelManager()
+    assert [mm.getLatestVersion(i) for i in range(p)] == [1 + T, 1 + T]
+    assert np.all(np.isfinite(L.get_params(0)))
+    L.close()
+
+
+def test_batched_actor_inference_vs_oracle(fi, oracle):
+    params = U.ac_params(21)
+    L = _ac_learner(fi, 4, 5, gemm_mode="simt")
+    L.set_params(0, params)
+    O = oracle.actor_critic(params)
+    obs = np.random.default_rng(2).standard_normal((70, 162)).astype(np.float32)
+    logits, values = L.infer(0, obs)
+    wl, wv = O.forward(obs)
+    assert U.rel_max(logits, wl) < TOL and U.rel_max(values, wv) < TOL
+    L.close()
+
+
+def test_create_rejects_bad_config(fi):
+    with pytest.raises(fi.FiError):
+        fi.Learner(1, 2, 5, 3)                                  # M > B (validateParameters)
+    with pytest.raises(fi.FiError):
+        fi.Learner(1, 4, 5, 2, model="mlp_actor_critic", loss="mse")
+    L = _ac_learner(fi, 2, 5, gemm_mode="simt")
+    bad = fi.Learner(1, 4, 6, 2, model="mlp_actor_critic", gemm_mode="simt")
+    with pytest.raises(fi.FiError):
+        L.trainModel(0, bad.stage_batch(0, np.zeros((2, 6 * 1024), np.uint8)))   # wrong slot size
+    L.close()
+    bad.close()
