@@ -68,7 +68,9 @@ struct Player {
     float *d_a = nullptr, *d_b = nullptr, *head = nullptr, *dhead = nullptr;
     void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;
     void* colsum_ws = nullptr; size_t colsum_ws_bytes = 0;
-    void* model_ws = nullptr;   // model-private extra workspace (farmer LSTM)
+    void* model_ws = nullptr;
+    void* farmer_ws = nullptr;      // FarmerWs (model_farmer.cu): training workspaces
+    void* farmer_inf_ws = nullptr;  // FarmerWs for batched inference
     unsigned char* stage_dev = nullptr;  // staged batch (fi_learner_stage_batch)
     unsigned char* stage_host = nullptr; // pinned bounce buffer for pageable sources
     size_t stage_bytes = 0;

@@ -1,9 +1,383 @@
-// FarmerLstm learner step (placeholder while the LSTM kernels land).
+// FarmerLstmModel learner step: the numerics the reference defines in
+// cmd/libtorch_bench/main.cpp:14-42 (model), :105-114 (criterion), :117-135 (train_step):
+//   lstm(z)[B,T,162 -> 128] -> h_{T-1} -> cat with x[B,484] -> 5 x (Linear + ReLU) -> Linear -> y[B,1]
+//   loss = mse / l1 / smooth_l1 (mean over the batch), backward through the dense stack and BPTT.
+// PyTorch LSTM conventions: gate row blocks i,f,g,o of the [4H, .] weights,
+// c' = f*c + i*g, h' = o*tanh(c'), h0 = c0 = 0, two bias vectors (both trainable).
+//
+// Layout: z is read straight out of the gathered batch (row (b,t) = record t of slot b, stride
+// 256 words); the input projection of all B*T rows is ONE GEMM; the recurrence runs in a
+// kernel that owns R batch rows per CTA for all T steps (rows are independent, so no inter-CTA
+// synchronisation); BPTT mirrors it and leaves the pre-activation gate gradients in place of
+// the gates, so dW_ih, dW_hh and the bias gradients are again single GEMMs / column sums.
 #include "learner.cuh"
+
 namespace fi {
-int farmer_alloc(fi_learner*, Player*) { return set_error(FI_ERR_STATE, "FarmerLstm step not available in this build"); }
-void farmer_free(Player*) {}
-int farmer_forward_backward(fi_learner*, Player*, const float*, int, int, int) { return set_error(FI_ERR_STATE, "FarmerLstm step not available in this build"); }
-int farmer_infer_alloc(fi_learner*, Player*, size_t, size_t) { return set_error(FI_ERR_STATE, "FarmerLstm step not available in this build"); }
-int farmer_infer(fi_learner*, Player*, const float*, const float*, const float*, size_t, size_t, float*, cudaStream_t) { return set_error(FI_ERR_STATE, "FarmerLstm step not available in this build"); }
+
+constexpr int kG4 = 4 * kLstmH;          // 512 gate columns
+constexpr int kFeat = kLstmH + kXDim;    // 612 = cat(h_last, x)
+constexpr int kLstmRows = 8;             // batch rows per CTA in the recurrent kernels
+constexpr int kLstmThreads = 512;
+
+struct FarmerWs {
+    float* gates = nullptr;   // [rows*T, 512]: x-projection -> post-activation gates -> gate gradients
+    float* hprev = nullptr;   // [rows*T, 128]: h_{t-1} (0 at t = 0)
+    float* cst = nullptr;     // [rows*T, 128]: c_t
+    float* whh_t = nullptr;   // [128, 512]: W_hh transposed (coalesced reads in the forward recurrence)
+    float* feat = nullptr;    // [rows, 612]
+    float* y = nullptr;       // [rows]
+    float* dy = nullptr;      // [rows]
+    float* target = nullptr;  // [rows]
+    float* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [rows, 512]
+    float *d_a = nullptr, *d_b = nullptr;  // [rows, 612]
+    void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;
+    void* colsum_ws = nullptr; size_t colsum_ws_bytes = 0;
+    size_t rows = 0, t = 0;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// out[k][j] = in[j][k] for the [512,128] recurrent weight
+__global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kG4 * kLstmH) {
+        const int j = i / kLstmH, k = i % kLstmH;
+        wt[k * kG4 + j] = w[i];
+    }
+}
+
+// feat[b, 128 + j] = x_j (64 words of x in each of the first 8 records), target[b] = aux of record 0
+__global__ void farmer_assemble_kernel(const float* __restrict__ batch, int m, int t, float* __restrict__ feat,
+                                       float* __restrict__ target) {
+    const int b = blockIdx.x;
+    const float* slot = batch + (size_t)b * t * kRecWords;
+    for (int j = threadIdx.x; j < kXDim; j += blockDim.x) {
+        const int rec = j / kXPerRec, off = j % kXPerRec;
+        feat[(size_t)b * kFeat + kLstmH + j] = rec < t ? __ldg(slot + (size_t)rec * kRecWords + kWX + off) : 0.f;
+    }
+    if (threadIdx.x == 0) target[b] = __ldg(slot + kWAux);
+}
+// inference variant: x is a dense [rows, 484] array
+__global__ void farmer_assemble_dense_kernel(const float* __restrict__ x, int m, float* __restrict__ feat) {
+    const int b = blockIdx.x;
+    for (int j = threadIdx.x; j < kXDim; j += blockDim.x) feat[(size_t)b * kFeat + kLstmH + j] = __ldg(x + (size_t)b * kXDim + j);
+}
+
+// Forward recurrence. gates[(b,t), 512] holds W_ih z + b_ih on entry and the post-activation
+// gates i,f,g,o on exit. Thread j owns gate column j; each CTA owns kLstmRows batch rows.
+__global__ void __launch_bounds__(kLstmThreads)
+lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, const float* __restrict__ b_hh,
+                    int m, int t, float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ feat) {
+    __shared__ float hs[kLstmRows][kLstmH];
+    __shared__ float cs[kLstmRows][kLstmH];
+    __shared__ float ps[kLstmRows][kG4];
+    const int j = threadIdx.x;
+    const int b0 = blockIdx.x * kLstmRows;
+    const int nrows = min(kLstmRows, m - b0);
+    for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) {
+        hs[i / kLstmH][i % kLstmH] = 0.f;
+        cs[i / kLstmH][i % kLstmH] = 0.f;
+    }
+    const float bias = __ldg(b_hh + j);
+    __syncthreads();
+    for (int s = 0; s < t; s++) {
+        float acc[kLstmRows];
+#pragma unroll
+        for (int r = 0; r < kLstmRows; r++)
+            acc[r] = r < nrows ? gates[((size_t)(b0 + r) * t + s) * kG4 + j] + bias : 0.f;
+#pragma unroll 8
+        for (int k = 0; k < kLstmH; k++) {
+            const float w = __ldg(whh_t + k * kG4 + j);
+#pragma unroll
+            for (int r = 0; r < kLstmRows; r++) acc[r] = fmaf(hs[r][k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kLstmRows; r++) ps[r][j] = acc[r];
+        __syncthreads();
+        // (row, unit) pairs: kLstmRows * 128 = 1024 over 512 threads
+        for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) {
+            const int r = i / kLstmH, u = i % kLstmH;
+            if (r < nrows) {
+                const float ig = sigmoidf_(ps[r][u]), fg = sigmoidf_(ps[r][kLstmH + u]);
+                const float gg = tanhf(ps[r][2 * kLstmH + u]), og = sigmoidf_(ps[r][3 * kLstmH + u]);
+                const float c = fmaf(fg, cs[r][u], ig * gg);
+                const float h = og * tanhf(c);
+                const size_t row = (size_t)(b0 + r) * t + s;
+                float* g = gates + row * kG4;
+                g[u] = ig; g[kLstmH + u] = fg; g[2 * kLstmH + u] = gg; g[3 * kLstmH + u] = og;
+                if (cst) cst[row * kLstmH + u] = c;
+                if (hprev) hprev[row * kLstmH + u] = hs[r][u];   // h_{s-1}
+                cs[r][u] = c;
+                ps[r][u] = h;  // parked: hs is still being read as h_{s-1} by other pairs of this pass
+                if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = h;
+            }
+        }
+        __syncthreads();
+        for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) hs[i / kLstmH][i % kLstmH] = ps[i / kLstmH][i % kLstmH];
+        __syncthreads();
+    }
+}
+
+// BPTT. On entry gates holds post-activation i,f,g,o; on exit the pre-activation gradients dG.
+// dfeat [m, ldf]: its first 128 columns are dL/dh_{T-1}.
+__global__ void __launch_bounds__(kLstmThreads)
+lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
+                     const float* __restrict__ dfeat, int ldf, int m, int t) {
+    __shared__ float dh[kLstmRows][kLstmH];
+    __shared__ float dc[kLstmRows][kLstmH];
+    __shared__ float dgs[kLstmRows][kG4];
+    __shared__ float part[4][kLstmRows][kLstmH];
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * kLstmRows;
+    const int nrows = min(kLstmRows, m - b0);
+    for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
+        const int r = i / kLstmH, u = i % kLstmH;
+        dh[r][u] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
+        dc[r][u] = 0.f;
+    }
+    __syncthreads();
+    const int q = tid >> 7, k = tid & 127;  // 4 groups of 128 gate rows x 128 hidden units
+    for (int s = t - 1; s >= 0; s--) {
+        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
+            const int r = i / kLstmH, u = i % kLstmH;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            if (r < nrows) {
+                const size_t row = (size_t)(b0 + r) * t + s;
+                float* g = gates + row * kG4;
+                const float ig = g[u], fg = g[kLstmH + u], gg = g[2 * kLstmH + u], og = g[3 * kLstmH + u];
+                const float tc = tanhf(cst[row * kLstmH + u]);
+                const float cp = s > 0 ? cst[(row - 1) * kLstmH + u] : 0.f;
+                const float dhv = dh[r][u];
+                const float dct = dc[r][u] + dhv * og * (1.f - tc * tc);
+                d0 = dct * gg * ig * (1.f - ig);
+                d1 = dct * cp * fg * (1.f - fg);
+                d2 = dct * ig * (1.f - gg * gg);
+                d3 = dhv * tc * og * (1.f - og);
+                g[u] = d0; g[kLstmH + u] = d1; g[2 * kLstmH + u] = d2; g[3 * kLstmH + u] = d3;
+                dc[r][u] = dct * fg;
+            }
+            dgs[r][u] = d0; dgs[r][kLstmH + u] = d1; dgs[r][2 * kLstmH + u] = d2; dgs[r][3 * kLstmH + u] = d3;
+        }
+        __syncthreads();
+        if (s > 0) {  // dh_{s-1}[r][k] = sum_j dG[r][j] W_hh[j][k]
+            float acc[kLstmRows];
+#pragma unroll
+            for (int r = 0; r < kLstmRows; r++) acc[r] = 0.f;
+#pragma unroll 8
+            for (int jj = 0; jj < kLstmH; jj++) {
+                const int jrow = q * kLstmH + jj;
+                const float w = __ldg(whh + (size_t)jrow * kLstmH + k);
+#pragma unroll
+                for (int r = 0; r < kLstmRows; r++) acc[r] = fmaf(dgs[r][jrow], w, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kLstmRows; r++) part[q][r][k] = acc[r];
+            __syncthreads();
+            for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
+                const int r = i / kLstmH, u = i % kLstmH;
+                dh[r][u] = (part[0][r][u] + part[1][r][u]) + (part[2][r][u] + part[3][r][u]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// criterion (main.cpp:105-114) and the seed of backward: dy = dloss_i/dy / denom (mean over the
+// GLOBAL batch). losses[0] += sum_i loss_i / denom (double).
+__global__ void regression_loss_kernel(const float* __restrict__ y, const float* __restrict__ target, int m, int kind,
+                                       double inv_denom, float* __restrict__ dy, double* __restrict__ losses) {
+    double local = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const float d = y[i] - target[i];
+        float g, l;
+        if (kind == FI_LOSS_MAE) {
+            g = (float)((d > 0.f) - (d < 0.f));
+            l = fabsf(d);
+        } else if (kind == FI_LOSS_HUBER) {  // smooth_l1_loss, beta = 1
+            if (fabsf(d) < 1.f) { g = d; l = 0.5f * d * d; }
+            else { g = (float)((d > 0.f) - (d < 0.f)); l = fabsf(d) - 0.5f; }
+        } else {
+            g = 2.f * d;
+            l = d * d;
+        }
+        dy[i] = (float)((double)g * inv_denom);
+        local += (double)l;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(losses, local * inv_denom);
+}
+
+// ------------------------------------------------------------------------------------------
+static void ws_release(FarmerWs* w) {
+    if (!w) return;
+    float* f[] = {w->gates, w->hprev, w->cst, w->whh_t, w->feat, w->y, w->dy, w->target, w->act[0], w->act[1], w->act[2],
+                  w->act[3], w->act[4], w->d_a, w->d_b};
+    for (float* p : f)
+        if (p) cudaFree(p);
+    if (w->gemm_ws) cudaFree(w->gemm_ws);
+    if (w->colsum_ws) cudaFree(w->colsum_ws);
+    delete w;
+}
+
+static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, FarmerWs** out) {
+    FarmerWs* w = new FarmerWs();
+    *out = w;
+    w->rows = rows;
+    w->t = t;
+    const size_t rt = rows * t;
+    FI_CUDA_OK(cudaMalloc((void**)&w->gates, rt * kG4 * sizeof(float)));
+    FI_CUDA_OK(cudaMalloc((void**)&w->whh_t, (size_t)kG4 * kLstmH * sizeof(float)));
+    FI_CUDA_OK(cudaMalloc((void**)&w->feat, rows * kFeat * sizeof(float)));
+    FI_CUDA_OK(cudaMalloc((void**)&w->y, rows * sizeof(float)));
+    for (int i = 0; i < 5; i++) FI_CUDA_OK(cudaMalloc((void**)&w->act[i], rows * kHid * sizeof(float)));
+    if (training) {
+        FI_CUDA_OK(cudaMalloc((void**)&w->hprev, rt * kLstmH * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->cst, rt * kLstmH * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->dy, rows * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->target, rows * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->d_a, rows * kFeat * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->d_b, rows * kFeat * sizeof(float)));
+        const int mode = l->cfg.gemm_mode;
+        size_t ws = 0;
+        auto upd = [&](size_t b) { if (b > ws) ws = b; };
+        upd(gemm_workspace_bytes(mode, 2, kG4, kZDim, (int)rt));
+        upd(gemm_workspace_bytes(mode, 2, kG4, kLstmH, (int)rt));
+        upd(gemm_workspace_bytes(mode, 2, kHid, kFeat, (int)rows));
+        upd(gemm_workspace_bytes(mode, 2, kHid, kHid, (int)rows));
+        upd(gemm_workspace_bytes(mode, 2, 1, kHid, (int)rows));
+        w->gemm_ws_bytes = ws;
+        if (ws) FI_CUDA_OK(cudaMalloc(&w->gemm_ws, ws));
+        w->colsum_ws_bytes = colsum_workspace_bytes((int)rt, kG4);
+        FI_CUDA_OK(cudaMalloc(&w->colsum_ws, w->colsum_ws_bytes));
+    }
+    return FI_OK;
+}
+
+int farmer_alloc(fi_learner* l, Player* p) {
+    FarmerWs* w = nullptr;
+    const int rc = ws_create(l, l->cfg.batch_size, l->cfg.entry_size, true, &w);
+    p->model_ws = nullptr;
+    p->farmer_ws = w;
+    return rc;
+}
+
+void farmer_free(Player* p) {
+    ws_release(static_cast<FarmerWs*>(p->farmer_ws));
+    ws_release(static_cast<FarmerWs*>(p->farmer_inf_ws));
+    p->farmer_ws = p->farmer_inf_ws = nullptr;
+}
+
+// z rows: (b,t) at z + (b*t + s) * ldz. Leaves y[m], feat, act (and the BPTT state when training).
+static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const float* z, int ldz, int m, int t,
+                          cudaStream_t st) {
+    const auto& T = l->tensors;
+    const int mode = l->cfg.gemm_mode;
+    const int rt = m * t;
+    {
+        LaunchScope ls("transpose_whh_kernel", st, 2.0 * 4 * kG4 * kLstmH, kWorkBytes);
+        transpose_whh_kernel<<<(kG4 * kLstmH + 255) / 256, 256, 0, st>>>(params + T[1].offset, w->whh_t);
+        FI_TRY(ls.done());
+    }
+    // gates = z W_ih^T + b_ih for all B*T rows at once
+    FI_TRY(launch_gemm(mode, 0, rt, kG4, kZDim, z, ldz, params + T[0].offset, kZDim, w->gates, kG4, params + T[2].offset,
+                       0, nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    {
+        // recurrent flops: 2 * 128 * 512 per (row, step)
+        LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
+        lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, 0, st>>>(
+            w->gates, w->whh_t, params + T[3].offset, m, t, w->hprev, w->cst, w->feat);
+        FI_TRY(ls.done());
+    }
+    const float* x = w->feat;
+    int k = kFeat;
+    for (int layer = 0; layer < 5; layer++) {
+        FI_TRY(launch_gemm(mode, 0, m, kHid, k, x, k, params + T[4 + 2 * layer].offset, k, w->act[layer], kHid,
+                           params + T[5 + 2 * layer].offset, 1, nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+        x = w->act[layer];
+        k = kHid;
+    }
+    return launch_gemm(mode, 0, m, 1, kHid, x, kHid, params + T[14].offset, kHid, w->y, 1, params + T[15].offset, 0,
+                       nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st);
+}
+
+int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int global_m) {
+    FarmerWs* w = static_cast<FarmerWs*>(p->farmer_ws);
+    if (!w) return set_error(FI_ERR_STATE, "farmer workspaces missing");
+    const auto& T = l->tensors;
+    const int mode = l->cfg.gemm_mode;
+    cudaStream_t st = p->stream;
+    float* g = p->grads;
+    {
+        LaunchScope ls("farmer_assemble_kernel", st, 2.0 * 4 * kXDim * (double)m, kWorkBytes);
+        farmer_assemble_kernel<<<m, 128, 0, st>>>(batch, m, t, w->feat, w->target);
+        FI_TRY(ls.done());
+    }
+    FI_TRY(farmer_forward(l, w, p->params, batch, kRecWords, m, t, st));
+    FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
+    {
+        LaunchScope ls("regression_loss_kernel", st, 12.0 * m, kWorkBytes);
+        regression_loss_kernel<<<(m + 255) / 256, 256, 0, st>>>(w->y, w->target, m, l->cfg.loss, 1.0 / (double)global_m,
+                                                              w->dy, p->d_losses);
+        FI_TRY(ls.done());
+    }
+    // dense6: dW = dy^T act4, db = sum dy, d4 = (dy W6) * relu'(act4)
+    FI_TRY(launch_colsum(w->dy, 1, m, 1, g + T[15].offset, w->colsum_ws, w->colsum_ws_bytes, st));
+    FI_TRY(launch_gemm(mode, 2, 1, kHid, m, w->dy, 1, w->act[4], kHid, g + T[14].offset, kHid, nullptr, 0, nullptr, 0,
+                       w->gemm_ws, w->gemm_ws_bytes, st));
+    float* d = w->d_a;
+    float* d_next = w->d_b;
+    FI_TRY(launch_gemm(mode, 1, m, kHid, 1, w->dy, 1, p->params + T[14].offset, kHid, d, kHid, nullptr, 0, w->act[4], kHid,
+                       w->gemm_ws, w->gemm_ws_bytes, st));
+    int ldd = kHid;
+    for (int layer = 4; layer >= 0; layer--) {
+        const float* in = layer == 0 ? w->feat : w->act[layer - 1];
+        const int k = layer == 0 ? kFeat : kHid;
+        FI_TRY(launch_colsum(d, ldd, m, kHid, g + T[5 + 2 * layer].offset, w->colsum_ws, w->colsum_ws_bytes, st));
+        FI_TRY(launch_gemm(mode, 2, kHid, k, m, d, ldd, in, k, g + T[4 + 2 * layer].offset, k, nullptr, 0, nullptr, 0,
+                           w->gemm_ws, w->gemm_ws_bytes, st));
+        // dgrad: into [m, k]; the ReLU mask of the producing layer, none for the feature row
+        FI_TRY(launch_gemm(mode, 1, m, k, kHid, d, ldd, p->params + T[4 + 2 * layer].offset, k, d_next, k, nullptr, 0,
+                           layer == 0 ? nullptr : w->act[layer - 1], kHid, w->gemm_ws, w->gemm_ws_bytes, st));
+        float* tmp = d; d = d_next; d_next = tmp;
+        ldd = k;
+    }
+    // d = dfeat [m, 612]; BPTT turns the stored gates into pre-activation gate gradients
+    {
+        LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
+        lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, 0, st>>>(w->gates, p->params + T[1].offset,
+                                                                                      w->cst, d, kFeat, m, t);
+        FI_TRY(ls.done());
+    }
+    const int rt = m * t;
+    FI_TRY(launch_gemm(mode, 2, kG4, kZDim, rt, w->gates, kG4, batch, kRecWords, g + T[0].offset, kZDim, nullptr, 0, nullptr,
+                       0, w->gemm_ws, w->gemm_ws_bytes, st));
+    FI_TRY(launch_gemm(mode, 2, kG4, kLstmH, rt, w->gates, kG4, w->hprev, kLstmH, g + T[1].offset, kLstmH, nullptr, 0,
+                       nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    FI_TRY(launch_colsum(w->gates, kG4, rt, kG4, g + T[2].offset, w->colsum_ws, w->colsum_ws_bytes, st));
+    FI_CUDA_OK(cudaMemcpyAsync(g + T[3].offset, g + T[2].offset, kG4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FI_OK;
+}
+
+int farmer_infer_alloc(fi_learner* l, Player* p, size_t rows, size_t t) {
+    ws_release(static_cast<FarmerWs*>(p->farmer_inf_ws));
+    FarmerWs* w = nullptr;
+    const int rc = ws_create(l, rows, t, false, &w);
+    p->farmer_inf_ws = w;
+    return rc;
+}
+
+int farmer_infer(fi_learner* l, Player* p, const float* params, const float* z_dev, const float* x_dev, size_t rows,
+                 size_t t, float* out_dev, cudaStream_t stream) {
+    FarmerWs* w = static_cast<FarmerWs*>(p->farmer_inf_ws);
+    if (!w || rows > w->rows || t > w->t) return set_error(FI_ERR_STATE, "farmer inference workspaces too small");
+    {
+        LaunchScope ls("farmer_assemble_dense_kernel", stream, 2.0 * 4 * kXDim * (double)rows, kWorkBytes);
+        farmer_assemble_dense_kernel<<<(unsigned)rows, 128, 0, stream>>>(x_dev, (int)rows, w->feat);
+        FI_TRY(ls.done());
+    }
+    FI_TRY(farmer_forward(l, w, params, z_dev, kZDim, (int)rows, (int)t, stream));
+    FI_CUDA_OK(cudaMemcpyAsync(out_dev, w->y, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return FI_OK;
+}
+
 }  // namespace fi

@@ -31,6 +31,7 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
     assert L.param_count == po.AC_PARAMS
     L.set_params(0, params)
     O = oracle.actor_critic(params, lr=5e-4)
+    parity = U.AdamParity(lr=5e-4)
     for s in range(steps):
         obs, mu, act, rew, disc, boot = U.vtrace_batch(100 + s, m, t, done_p=0.03)
         slots = po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)
@@ -40,9 +41,10 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
         got = L.last_losses(0)
         np.testing.assert_allclose(got, want, rtol=TOL, atol=1e-6 * abs(want[0]))
         assert U.rel_l2(L.get_grads(0), O.grads()) < TOL
+        parity.observe(O.grads())
         L.apply_update(0)
         O.opt_step()
-        assert U.rel_l2(L.get_params(0), O.params()) < TOL
+        parity.check(L.get_params(0), O.params(), TOL)
     assert L.steps_done(0) == steps
     L.close()
 
@@ -168,3 +170,70 @@ def test_create_rejects_bad_config(fi):
         L.trainModel(0, bad.stage_batch(0, np.zeros((2, 6 * 1024), np.uint8)))   # wrong slot size
     L.close()
     bad.close()
+
+
+# ------------------------------------------------------------------------------- FarmerLstm step
+def _farmer_learner(fi, m, t, **kw):
+    return fi.Learner(1, max(m, 2), t, m, 0, 0, "", "", 0, model="farmer_lstm", **kw)
+
+
+@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("ci", [3, 4, 5, 6])
+def test_farmer_step_vs_reference_golden(fi, oracle, ci, gemm_mode):
+    """The CUDA FarmerLstm step against the reference's own libtorch train_step
+    (cmd/libtorch_bench/main.cpp:117-135; fixtures from tools/make_golden.py). Case 3 is the README
+    shape / BASELINE.json configs[0]: batch 64, seq 100, MSE, Adam lr 5e-4."""
+    g = np.load(os.path.join(U.GOLDEN, "farmer_step.npz"))
+    stride = int(g["stride"][0])
+    b, t, steps, ps, ys, bs = (int(v) for v in g[f"c{ci}_meta"])
+    loss, opt = (str(v) for v in g[f"c{ci}_kind"])
+    lr = float(g[f"c{ci}_lr"][0])
+    params = U.farmer_params(ps)
+    L = _farmer_learner(fi, b, t, loss=loss, optimizer=opt, lr=lr, gemm_mode=gemm_mode)
+    assert L.param_count == po.FARMER_PARAMS and len(L.tensor_table()) == 16
+    L.set_params(0, params)
+    O = oracle.farmer(params, opt=opt, lr=lr, loss=loss)
+    z0, x0, _ = U.farmer_batch(ys, b, t)
+    np.testing.assert_allclose(L.infer(0, z0, x0), g[f"c{ci}_y0"], rtol=2e-5, atol=2e-6)
+    parity = U.AdamParity(lr=lr)
+    for s in range(steps):
+        z, x, tg = U.farmer_batch(bs + s, b, t)
+        batch = L.stage_batch(0, po.pack_farmer_slots(z, x, tg))
+        L.forward_backward(0, batch)
+        want_loss = float(g[f"c{ci}_losses"][s])
+        assert abs(L.last_losses(0)[0] - want_loss) <= TOL * abs(want_loss) + 1e-7
+        O.loss_grad(z, x, tg)
+        assert U.rel_l2(L.get_grads(0)[::stride], g[f"c{ci}_grads"][s]) < 2e-5      # vs the reference (fp32)
+        assert U.rel_l2(L.get_grads(0), O.grads()) < TOL                            # vs the float64 oracle
+        parity.observe(O.grads())
+        L.apply_update(0)
+        O.opt_step()
+    if opt == "sgd":
+        assert U.rel_l2(L.get_params(0), O.params()) < TOL
+    else:
+        parity.check(L.get_params(0), O.params(), TOL)
+    # against the reference's own parameters after N steps (every 997th element is stored)
+    got, want, mask = L.get_params(0)[::stride], g[f"c{ci}_params"], parity.mask[::stride]
+    assert np.linalg.norm((got - want)[mask]) / np.linalg.norm(want[mask]) < TOL
+    L.close()
+
+
+def test_farmer_step_through_ring_decodes_records(fi, oracle):
+    """Batch assembly + record decode: trajectories written through the ring give the oracle's loss."""
+    b, t = 6, 10
+    params = U.farmer_params(5)
+    L = _farmer_learner(fi, b, t, gemm_mode="simt")
+    L.set_params(0, params)
+    z, x, tg = U.farmer_batch(77, b, t)
+    slots = po.pack_farmer_slots(z, x, tg)
+    ring = L.getSharedBuffers()[0]
+    for i in range(b):
+        assert ring.write(slots[i])
+    batch = ring.readBatch(b)
+    dz, dx, dt = oracle.decode_farmer(batch.to_host(), b, t)
+    assert np.array_equal(dz, z) and np.array_equal(dx, x) and np.array_equal(dt, tg)
+    L.forward_backward(0, batch)
+    O = oracle.farmer(params)
+    want = O.loss_grad(z, x, tg)
+    assert abs(L.last_losses(0)[0] - want) <= TOL * abs(want)
+    L.close()

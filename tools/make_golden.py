@@ -30,7 +30,9 @@ SAMPLE_STRIDE = 997  # every 997th parameter/gradient is stored
 def farmer_fixture():
     out = {}
     cases = [("mse", "adam", 5e-4, 4, 6, 3), ("mae", "sgd", 1e-2, 3, 5, 2), ("huber", "adamw", 5e-4, 5, 4, 2),
-             ("mse", "adam", 5e-4, 64, 100, 2)]  # the last one is the README shape (configs[0])
+             ("mse", "adam", 5e-4, 64, 100, 2),  # the README shape (configs[0])
+             # T >= 8 so that the 1024-byte record layout can carry x (8 records x 64 words): GPU cases
+             ("mae", "sgd", 1e-2, 3, 9, 2), ("huber", "adamw", 5e-4, 5, 8, 3), ("mse", "adam", 5e-4, 9, 33, 3)]
     for ci, (loss, opt, lr, b, t, steps) in enumerate(cases):
         r = po.RefNN(seed=1, opt=opt, lr=lr, loss=loss)
         p0 = U.farmer_params(100 + ci)
