@@ -79,37 +79,46 @@ def rel_max(a, b) -> float:
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def trimmed_rel_l2(a, b, drop_frac=0.005) -> float:
+    """Relative L2 over all but the `drop_frac` worst elements (see AdamParity)."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    d = np.abs(a - b)
+    keep = max(1, int(np.ceil(d.size * (1.0 - drop_frac))))
+    idx = np.argpartition(d, keep - 1)[:keep]
+    return float(np.linalg.norm(d[idx]) / max(np.linalg.norm(b[idx]), 1e-300))
+
+
 class AdamParity:
     """Parameter parity after N optimiser steps, honest about Adam's conditioning.
 
     Adam's update is lr * m / (sqrt(v) + eps): on the first steps that is ~ lr * sign(g), so an element
-    whose gradient is smaller than the fp32 noise of the computation (|g| <~ 1e-6 * rms(g); a handful
-    per million) can move by up to 2*lr in the opposite direction of the float64 oracle while every
-    gradient agrees to 1e-6. One such element among 1e6 already costs ~4e-5 of relative L2. The
-    north_star tolerance (relative error <= 1e-5) is therefore asserted over the elements whose
-    gradient was well above the noise floor at EVERY step (|g| > tau * rms(g), tau = 1e-3: ~99.9 % of
-    the non-dead parameters); the remaining elements must stay within the bounded update (2 * lr per
-    step), and the relative L2 over ALL parameters is checked at 1e-3.
+    whose gradient is comparable to the fp32 noise of the computation can move by up to 2*lr in the
+    opposite direction of the float64 oracle while every gradient agrees to 1e-6 (one such element
+    among 1e6 already costs ~4e-5 of relative L2; libtorch's own fp32 step shows the same effect
+    against float64). The north_star tolerance (relative error <= 1e-5 after N steps) is therefore
+    asserted two ways:
+      * teacher-forced: a float64 oracle that is fed the CUDA gradients each step must end with the
+        same parameters, ALL elements, relative L2 <= 1e-5 (the gradients themselves are compared at
+        1e-5 against the oracle's own at every step, at the same parameters);
+      * free-running: an independent float64 oracle; relative L2 <= 1e-5 over all but the 0.5 % worst
+        elements (the sign-flip candidates), and <= 1e-3 over everything (bounded update 2*lr/step).
     """
 
-    def __init__(self, lr: float, tau: float = 1e-3):
-        self.lr, self.tau, self.mask, self.steps = lr, tau, None, 0
+    def __init__(self, forced, free):
+        self.forced, self.free = forced, free
 
-    def observe(self, oracle_grads):
-        g = np.abs(np.asarray(oracle_grads, np.float64))
-        nz = g[g > 0]
-        rms = np.sqrt((nz ** 2).mean()) if nz.size else 0.0
-        ok = (g > self.tau * rms) | (g == 0)        # exact zeros (dead units) stay exact on both sides
-        self.mask = ok if self.mask is None else (self.mask & ok)
-        self.steps += 1
+    def step(self, cuda_grads):
+        """Call after both oracles ran loss_grad on this step's batch."""
+        self.forced.set_grads(np.asarray(cuda_grads, np.float64))
+        self.forced.opt_step()
+        self.free.opt_step()
 
-    def check(self, got, want, tol=1e-5):
-        got = np.asarray(got, np.float64)
-        want = np.asarray(want, np.float64)
-        m = self.mask
-        assert m.mean() > 0.99, m.mean()
-        err_ok = np.linalg.norm((got - want)[m]) / np.linalg.norm(want[m])
-        assert err_ok < tol, f"well-conditioned parameters differ: rel l2 {err_ok:.3e}"
-        assert np.abs(got - want)[~m].max(initial=0.0) <= 2.0 * self.lr * self.steps * 1.01
-        assert rel_l2(got, want) < 1e-3
-        return err_ok
+    def check(self, cuda_params, tol=1e-5):
+        e_forced = rel_l2(cuda_params, self.forced.params())
+        assert e_forced < tol, f"teacher-forced parameters differ: rel l2 {e_forced:.3e}"
+        e_trim = trimmed_rel_l2(cuda_params, self.free.params())
+        assert e_trim < tol, f"free-running parameters differ (99.5 % best): rel l2 {e_trim:.3e}"
+        e_all = rel_l2(cuda_params, self.free.params())
+        assert e_all < 1e-3, f"free-running parameters differ: rel l2 {e_all:.3e}"
+        return e_forced, e_trim, e_all
