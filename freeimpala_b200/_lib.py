@@ -74,6 +74,7 @@ SIGNATURES = {
     "fi_learner_last_losses_f64": (c_int, [_P, c_int, C.POINTER(c_double)]),
     "fi_learner_sync": (c_int, [_P, c_int]),
     "fi_learner_steps_done": (c_u64, [_P, c_int]),
+    "fi_learner_debug_relu_masks": (c_int, [_P, c_int, _P, c_size_t]),
     "fi_learner_param_count": (c_size_t, [_P]),
     "fi_learner_num_tensors": (c_int, [_P]),
     "fi_learner_tensor_info": (c_int, [_P, c_int] + [C.POINTER(c_size_t)] * 4),

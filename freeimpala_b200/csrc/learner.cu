@@ -753,6 +753,40 @@ int fi_learner_dp_init(fi_learner* l, const void* ids, int rank, int world_size)
 }
 int fi_learner_dp_world(const fi_learner* l) { return l ? l->dp_world : 0; }
 
+// ---- inspection (parity tests) ---------------------------------------------------------------
+__global__ void relu_mask_kernel(const float* __restrict__ a, const float* __restrict__ lo, size_t n,
+                                 unsigned char* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (a[i] > 0.f || (lo && lo[i] > 0.f)) ? 1 : 0;
+}
+
+int fi_learner_debug_relu_masks(fi_learner* l, int player, unsigned char* host, size_t n) {
+    Player* p = get_player(l, player);
+    if (!p || !host) return set_error(FI_ERR_ARG, "fi_learner_debug_relu_masks: null argument");
+    const bool farmer = l->cfg.model == FI_MODEL_FARMER_LSTM;
+    const size_t rows = farmer ? p->last_rows / l->cfg.entry_size : p->last_rows;
+    const size_t per_layer = rows * fi::kHid;
+    if (rows == 0 || n != 5 * per_layer)
+        return set_error(FI_ERR_ARG, "fi_learner_debug_relu_masks: need n = 5 * %zu (rows of the last step x 512)", per_layer);
+    FI_CUDA_OK(cudaSetDevice(l->cfg.device));
+    std::lock_guard<std::mutex> step_lock(p->step_mu);
+    unsigned char* dev = nullptr;
+    FI_CUDA_OK(cudaMalloc((void**)&dev, n));
+    int rc = FI_OK;
+    for (int layer = 0; layer < 5 && rc == FI_OK; layer++) {
+        const float *a = nullptr, *lo = nullptr;
+        rc = farmer ? fi::farmer_activation(p, layer, &a, &lo) : fi::ac_activation(p, layer, &a, &lo);
+        if (rc != FI_OK) break;
+        fi::LaunchScope ls("relu_mask_kernel", p->stream, 5.0 * per_layer, fi::kWorkBytes);
+        relu_mask_kernel<<<fi::kNumSMs * 4, 256, 0, p->stream>>>(a, lo, per_layer, dev + layer * per_layer);
+        rc = ls.done();
+    }
+    if (rc == FI_OK && cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) rc = FI_ERR_CUDA;
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess && rc == FI_OK) rc = set_error(FI_ERR_CUDA, "stream sync failed");
+    cudaFree(dev);
+    return rc;
+}
+
 // ---- instrumentation ------------------------------------------------------------------------
 void fi_prof_enable(int on) {
     fi::ProfState& p = fi::prof();

@@ -88,6 +88,13 @@ int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int
     return FI_OK;
 }
 
+int ac_activation(Player* p, int layer, const float** a, const float** lo) {
+    if (layer < 0 || layer >= (int)p->act.size()) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
+    *a = p->act[layer];
+    *lo = nullptr;
+    return FI_OK;
+}
+
 int ac_infer_alloc(fi_learner* /*l*/, Player* p, size_t rows) {
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.assign(5, nullptr);

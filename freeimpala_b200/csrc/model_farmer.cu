@@ -358,6 +358,14 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
     return FI_OK;
 }
 
+int farmer_activation(Player* p, int layer, const float** a, const float** lo) {
+    FarmerWs* w = static_cast<FarmerWs*>(p->farmer_ws);
+    if (!w || layer < 0 || layer >= 5) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
+    *a = w->act[layer];
+    *lo = nullptr;
+    return FI_OK;
+}
+
 int farmer_infer_alloc(fi_learner* l, Player* p, size_t rows, size_t t) {
     ws_release(static_cast<FarmerWs*>(p->farmer_inf_ws));
     FarmerWs* w = nullptr;

@@ -200,6 +200,12 @@ class Learner:
         check(self._lib.fi_learner_last_losses_f64(self._h, player_index, out), "fi_learner_last_losses_f64")
         return np.array(list(out))
 
+    def debug_relu_masks(self, player_index: int, rows: int) -> np.ndarray:
+        out = np.empty((5, rows * 512), np.uint8)
+        check(self._lib.fi_learner_debug_relu_masks(self._h, player_index, out.ctypes.data, out.size),
+              "fi_learner_debug_relu_masks")
+        return out
+
     def steps_done(self, player_index: int) -> int:
         return self._lib.fi_learner_steps_done(self._h, player_index)
 

@@ -184,6 +184,11 @@ FI_API int fi_learner_last_losses_f64(fi_learner* l, int player, double losses[4
 FI_API int fi_learner_sync(fi_learner* l, int player);
 FI_API uint64_t fi_learner_steps_done(fi_learner* l, int player);
 
+/* Inspection for parity tests: the ReLU decisions (1 = active) of the 5 hidden layers in the last
+ * forward pass of this player, [5][rows * 512] bytes (rows = M*T for the actor-critic model, M for
+ * the farmer model's dense stack). */
+FI_API int fi_learner_debug_relu_masks(fi_learner* l, int player, unsigned char* host, size_t n);
+
 /* Flat fp32 parameter arena, in the reference's model.parameters() order (farmer: 16
  * tensors, 1,514,497 values = 6,057,988 bytes). */
 FI_API size_t fi_learner_param_count(const fi_learner* l);

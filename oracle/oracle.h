@@ -119,6 +119,16 @@ void orc_ac_tensor_table(int64_t offsets[ORC_AC_TENSORS], int64_t numels[ORC_AC_
 void orc_ac_loss_grad(orc_ac* f, const float* obs, const float* mu_logits, const int32_t* action,
                       const float* reward, const float* discount, const float* bootstrap, int m,
                       int t, double* out_losses);
+/* Same, with the ReLU decisions of the 5 hidden layers supplied by the caller: relu_mask is
+ * [5][m*t*512] bytes (non-zero = unit active). The GPU parity tests pass the CUDA run's own decisions
+ * so that units whose pre-activation lies within fp32 rounding of zero (where an fp32 and a float64
+ * forward legitimately disagree, and one disagreement changes a weight-gradient row by O(1/rows)) are
+ * pinned. *n_override = units where the mask differs from z > 0; *max_override = largest |z|/rms(z)
+ * among those (the test asserts both are tiny). */
+void orc_ac_loss_grad_masked(orc_ac* f, const float* obs, const float* mu_logits, const int32_t* action,
+                             const float* reward, const float* discount, const float* bootstrap, int m,
+                             int t, double* out_losses, const uint8_t* relu_mask, int64_t* n_override,
+                             double* max_override);
 void orc_ac_forward(orc_ac* f, const float* obs, int rows, double* logits, double* value);
 void orc_ac_opt_step(orc_ac* f);
 void orc_ac_get_params(const orc_ac* f, double* out);

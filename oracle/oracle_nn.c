@@ -416,13 +416,39 @@ void orc_ac_opt_step(orc_ac* f) {
     orc_opt_update(f->opt_kind, f->lr, f->step, ORC_AC_PARAMS, f->p, f->g, f->m, f->v);
 }
 
+/* Forward. gate[l] (may be NULL) receives the ReLU decisions as 1.0 / 0.0. With `mask` ([5][rows*HID]
+ * bytes, may be NULL) the decisions are taken from the caller instead of z > 0 -- used by the GPU parity
+ * tests to pin the units whose pre-activation lies within fp32 rounding of the kink, where an fp32 and
+ * a float64 forward legitimately disagree; *n_override counts the units where the mask differs from
+ * z > 0 and *max_override is the largest |z| / rms(z of that layer) among them. */
 static void ac_fwd(const orc_ac* f, const float* obs, int rows, double* in0, double* act[5],
-                   double* head) {
+                   double* head, double* gate[5], const uint8_t* mask, int64_t* n_override,
+                   double* max_override) {
     for (size_t i = 0; i < (size_t)rows * ZD; i++) in0[i] = (double)obs[i];
     const double* in = in0;
     int k = ZD;
+    if (n_override) *n_override = 0;
+    if (max_override) *max_override = 0.0;
     for (int l = 0; l < 5; l++) {
-        dense_fwd(in, k, f->p + f->off[2 * l], f->p + f->off[2 * l + 1], rows, HID, k, act[l], 1);
+        const size_t n = (size_t)rows * HID;
+        dense_fwd(in, k, f->p + f->off[2 * l], f->p + f->off[2 * l + 1], rows, HID, k, act[l], 0);
+        double ss = 0.0;
+        for (size_t i = 0; i < n; i++) ss += act[l][i] * act[l][i];
+        const double rms = sqrt(ss / (double)n) + 1e-300;
+        for (size_t i = 0; i < n; i++) {
+            const double z = act[l][i];
+            int on = z > 0.0;
+            if (mask) {
+                const int want = mask[(size_t)l * n + i] != 0;
+                if (want != on) {
+                    if (n_override) (*n_override)++;
+                    if (max_override && fabs(z) / rms > *max_override) *max_override = fabs(z) / rms;
+                    on = want;
+                }
+            }
+            act[l][i] = on ? z : 0.0;
+            if (gate) gate[l][i] = on ? 1.0 : 0.0;
+        }
         in = act[l];
         k = HID;
     }
@@ -434,7 +460,7 @@ void orc_ac_forward(orc_ac* f, const float* obs, int rows, double* logits, doubl
     double* act[5];
     for (int l = 0; l < 5; l++) act[l] = (double*)malloc(sizeof(double) * (size_t)rows * HID);
     double* head = (double*)malloc(sizeof(double) * (size_t)rows * NHEAD);
-    ac_fwd(f, obs, rows, in0, act, head);
+    ac_fwd(f, obs, rows, in0, act, head, NULL, NULL, NULL, NULL);
     for (int i = 0; i < rows; i++) {
         for (int a = 0; a < NA; a++) logits[(size_t)i * NA + a] = head[(size_t)i * NHEAD + a];
         value[i] = head[(size_t)i * NHEAD + NA];
@@ -443,15 +469,19 @@ void orc_ac_forward(orc_ac* f, const float* obs, int rows, double* logits, doubl
     for (int l = 0; l < 5; l++) free(act[l]);
 }
 
-void orc_ac_loss_grad(orc_ac* f, const float* obs, const float* mu_logits, const int32_t* action,
-                      const float* reward, const float* discount, const float* bootstrap, int m,
-                      int t, double* out_losses) {
+void orc_ac_loss_grad_masked(orc_ac* f, const float* obs, const float* mu_logits, const int32_t* action,
+                             const float* reward, const float* discount, const float* bootstrap, int m,
+                             int t, double* out_losses, const uint8_t* relu_mask, int64_t* n_override,
+                             double* max_override) {
     const int rows = m * t;
     double* in0 = (double*)malloc(sizeof(double) * (size_t)rows * ZD);
-    double* act[5];
-    for (int l = 0; l < 5; l++) act[l] = (double*)malloc(sizeof(double) * (size_t)rows * HID);
+    double *act[5], *gate[5];
+    for (int l = 0; l < 5; l++) {
+        act[l] = (double*)malloc(sizeof(double) * (size_t)rows * HID);
+        gate[l] = (double*)malloc(sizeof(double) * (size_t)rows * HID);
+    }
     double* head = (double*)malloc(sizeof(double) * (size_t)rows * NHEAD);
-    ac_fwd(f, obs, rows, in0, act, head);
+    ac_fwd(f, obs, rows, in0, act, head, gate, relu_mask, n_override, max_override);
 
     double* logits = (double*)malloc(sizeof(double) * (size_t)rows * NA);
     double* value = (double*)malloc(sizeof(double) * (size_t)rows);
@@ -472,18 +502,25 @@ void orc_ac_loss_grad(orc_ac* f, const float* obs, const float* mu_logits, const
     double* da = (double*)malloc(sizeof(double) * (size_t)rows * HID);
     double* db_ = (double*)malloc(sizeof(double) * (size_t)rows * HID);
     dense_wgrad(dhead, act[4], HID, rows, NHEAD, HID, f->g + f->off[10], f->g + f->off[11]);
-    dense_dgrad(dhead, f->p + f->off[10], rows, NHEAD, HID, da, act[4]);
+    dense_dgrad(dhead, f->p + f->off[10], rows, NHEAD, HID, da, gate[4]);
     for (int l = 4; l >= 0; l--) {
         const double* in = l == 0 ? in0 : act[l - 1];
         int k = l == 0 ? ZD : HID;
         dense_wgrad(da, in, k, rows, HID, k, f->g + f->off[2 * l], f->g + f->off[2 * l + 1]);
         if (l > 0) {
-            dense_dgrad(da, f->p + f->off[2 * l], rows, HID, HID, db_, act[l - 1]);
+            dense_dgrad(da, f->p + f->off[2 * l], rows, HID, HID, db_, gate[l - 1]);
             double* tmp = da; da = db_; db_ = tmp;
         }
     }
     free(in0); free(head); free(logits); free(value); free(dlogits); free(dvalue); free(da); free(db_);
-    for (int l = 0; l < 5; l++) free(act[l]);
+    for (int l = 0; l < 5; l++) { free(act[l]); free(gate[l]); }
+}
+
+void orc_ac_loss_grad(orc_ac* f, const float* obs, const float* mu_logits, const int32_t* action,
+                      const float* reward, const float* discount, const float* bootstrap, int m,
+                      int t, double* out_losses) {
+    orc_ac_loss_grad_masked(f, obs, mu_logits, action, reward, discount, bootstrap, m, t, out_losses,
+                            NULL, NULL, NULL);
 }
 
 /* Threads the OpenMP loops above use (bench.py reports it as cpu_baseline.cores). */

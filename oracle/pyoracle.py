@@ -98,6 +98,7 @@ class Oracle:
         L.orc_ac_destroy.argtypes = [C.c_void_p]
         L.orc_ac_tensor_table.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_ac_loss_grad.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int] * 2 + [C.c_void_p]
+        L.orc_ac_loss_grad_masked.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int] * 2 + [C.c_void_p] * 2 + [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.orc_ac_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_ac_opt_step.argtypes = [C.c_void_p]
 
@@ -289,6 +290,20 @@ class OracleAC:
         losses = np.empty(4, np.float64)
         self.o.lib.orc_ac_loss_grad(self.h, _p(obs), _p(mu), _p(act), _p(rew), _p(disc), _p(boot), m, t, _p(losses))
         return losses
+
+    def loss_grad_masked(self, obs, mu, act, rew, disc, boot, relu_mask):
+        """loss_grad with the ReLU decisions pinned to `relu_mask` ([5, m*t*512] uint8). Returns
+        (losses, number of overridden units, largest |z|/rms among them)."""
+        obs, mu, rew, disc, boot = map(_f32, (obs, mu, rew, disc, boot))
+        act = np.ascontiguousarray(act, dtype=np.int32)
+        relu_mask = np.ascontiguousarray(relu_mask, dtype=np.uint8)
+        m, t = act.shape
+        assert relu_mask.size == 5 * m * t * 512
+        losses = np.empty(4, np.float64)
+        n_over, max_over = C.c_int64(), C.c_double()
+        self.o.lib.orc_ac_loss_grad_masked(self.h, _p(obs), _p(mu), _p(act), _p(rew), _p(disc), _p(boot), m, t,
+                                           _p(losses), _p(relu_mask), C.byref(n_over), C.byref(max_over))
+        return losses, n_over.value, max_over.value
 
     def opt_step(self):
         self.o.lib.orc_ac_opt_step(self.h)

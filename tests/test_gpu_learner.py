@@ -36,11 +36,17 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
     for s in range(steps):
         obs, mu, act, rew, disc, boot = U.vtrace_batch(100 + s, m, t, done_p=0.03)
         slots = po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)
-        want = O.loss_grad(obs, mu, act, rew, disc, boot)
         want_free = F.loss_grad(obs, mu, act, rew, disc, boot)
         batch = L.stage_batch(0, slots)
         L.forward_backward(0, batch)
         got = L.last_losses(0)
+        # ReLU kinks: a unit whose pre-activation is within fp32 rounding of zero is legitimately decided
+        # differently by an fp32 and a float64 forward, and ONE such unit changes a weight-gradient row by
+        # O(1/rows) (measured: 7e-4 of ||dW1|| at 64 x 100). The oracle therefore takes the CUDA run's ReLU
+        # decisions; the assertions below prove that only genuinely ambiguous units were overridden.
+        masks = L.debug_relu_masks(0, m * t)
+        want, n_over, max_over = O.loss_grad_masked(obs, mu, act, rew, disc, boot, masks)
+        assert n_over <= 4 + 2e-5 * masks.size and max_over < 1e-5, (n_over, max_over)
         np.testing.assert_allclose(got, want, rtol=TOL, atol=1e-6 * abs(want[0]))
         np.testing.assert_allclose(got, want_free, rtol=TOL, atol=1e-6 * abs(want[0]))
         grads = L.get_grads(0)
