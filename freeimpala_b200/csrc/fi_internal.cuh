@@ -24,6 +24,27 @@ int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* works
                   cudaStream_t stream);
 size_t colsum_workspace_bytes(int m, int n);
 
+// out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).
+int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream);
+
+// ---- tcgen05 3xTF32 path (gemm_tc.cu) -----------------------------------------------------------
+// An fp32 matrix carried as the exact pair x = hi + lo (hi: low 13 mantissa bits cleared), row stride ld.
+struct SplitMat {
+    const float* hi;
+    const float* lo;
+    int ld;
+};
+struct TcOut {
+    float* c; int ldc;                       // plain fp32 output (may be null)
+    float* c_hi; float* c_lo; int ld_split;  // hi/lo output for the next GEMM (may be null)
+    int transpose;                           // plain output written as c[col * ldc + row]
+};
+int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st);
+int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,
+                         const float* mask, int ldmask, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k);
+bool gemm_tc_available();
+
 // Dispatching GEMM (gemm.cu): picks the tcgen05 3xTF32 kernel or the SIMT kernel per fi_gemm_mode.
 int launch_gemm(int mode, int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c,
                 int ldc, const float* bias, int relu, const float* mask, int ldmask, void* workspace,

@@ -21,7 +21,10 @@ int launch_gemm(int mode, int trans, int m, int n, int k, const float* a, int ld
                 int ldc, const float* bias, int relu, const float* mask, int ldmask, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream) {
     if (mode != FI_GEMM_SIMT) {
-        if (gemm_tc_supported(trans, m, n, k, a, lda, b, ldb, c, ldc))
+        // AUTO: the tensor-core path pays a split pre-pass for plain fp32 operands; use it from ~64 MFLOP up
+        const bool big = 2.0 * (double)m * (double)n * (double)k >= 64e6;
+        if ((mode == FI_GEMM_TCGEN05 || big) && gemm_tc_supported(trans, m, n, k, a, lda, b, ldb, c, ldc) &&
+            (mode == FI_GEMM_TCGEN05 || (workspace && workspace_bytes >= gemm_tc_workspace_bytes(trans, m, n, k))))
             return launch_gemm_tc(trans, m, n, k, a, lda, b, ldb, c, ldc, bias, relu, mask, ldmask, workspace,
                                   workspace_bytes, stream);
         if (mode == FI_GEMM_TCGEN05)

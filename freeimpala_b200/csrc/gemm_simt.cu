@@ -250,6 +250,15 @@ colsum_partial_kernel(const float* __restrict__ x, int ldx, int m, int n, int ro
     }
 }
 
+int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    LaunchScope lr("reduce_splits_kernel", stream, 4.0 * (double)n * (splits + 1), kWorkBytes);
+    reduce_splits_kernel<<<blocks, 256, 0, stream>>>(partial, splits, stride, n, out);
+    return lr.done();
+}
+
 static int pick_splits(int tiles, int k, int max_splits) {
     // enough CTAs for ~2 waves of 148 SMs, at least 256 reduction steps per split
     int want = (2 * kNumSMs + tiles - 1) / tiles;

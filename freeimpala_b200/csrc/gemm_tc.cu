@@ -1,12 +1,554 @@
-// tcgen05 3xTF32 GEMM (placeholder until the kernel lands: reports "unsupported" so the
-// dispatcher uses the SIMT path; FI_GEMM_TCGEN05 then fails loudly).
+// tcgen05 3xTF32 GEMM for sm_100a: fp32-accurate products on the 5th-generation tensor cores.
+//
+// The learner's tolerance (parameters within 1e-5 of an fp32/float64 reference) rules out plain
+// TF32 / bf16 operands, so every fp32 operand x is carried as an exact pair
+//     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
+//                    lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits),
+// and each product is issued as three kind::tf32 MMAs into the same fp32 TMEM accumulator:
+//     D += A_hi B_hi + A_hi B_lo + A_lo B_hi        (the dropped A_lo B_lo term is ~2^-22 relative).
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles; 256 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A_hi, A_lo, B_hi, B_lo into a
+//              multi-stage shared-memory ring, completion on mbarriers;
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=8) x 4 k-slices x 3 products
+//              per 32-wide k-block, tcgen05.commit releases the stage / publishes the accumulator;
+//   warp 2     TMEM allocator (2 accumulator stages of BN fp32 columns, so the epilogue of tile i overlaps the
+//              MMAs of tile i+1);
+//   warps 4-7  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / ReLU-mask, then either a plain
+//              fp32 store or the hi/lo split store that feeds the next GEMM.
+// Operand layouts (UMMA "major"): K-major tiles are [rows][32 k] with one 128-byte row per matrix row;
+// MN-major tiles are [32 k][32 mn] boxes (the reduction index is the slow one), so dgrad (B = W[n,k] read along
+// n) and wgrad (both operands read along the batch rows) need no transposed copies.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "fi_internal.cuh"
 
 namespace fi {
-bool gemm_tc_supported(int, int, int, int, const float*, int, const float*, int, const float*, int) { return false; }
-size_t gemm_tc_workspace_bytes(int, int, int, int) { return 0; }
-int launch_gemm_tc(int, int, int, int, const float*, int, const float*, int, float*, int, const float*, int,
-                   const float*, int, void*, size_t, cudaStream_t) {
-    return set_error(FI_ERR_STATE, "tcgen05 GEMM not available in this build");
+
+constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int kTcThreads = 256;
+constexpr int kTcSmemLimit = 227 * 1024;
+
+struct TcEpilogue {
+    float* c;            // plain fp32 output (may be null)
+    int ldc;
+    float* c_hi;         // split output (may be null)
+    float* c_lo;
+    int ldc_split;
+    const float* bias;   // [n] or null
+    const float* mask;   // [m, ldmask]: out = mask > 0 ? out : 0 (ReLU backward), or null
+    int ldmask;
+    int relu;
+    int transpose_out;   // c[col * ldc + row] (plain output only)
+    size_t split_stride; // elements between split-K slabs of c
+};
+
+struct TcShape {
+    int m, n, k;
+    int num_m_blocks, num_n_blocks, num_splits, kb_per_split, num_kb;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        // a pipeline bug must surface as a launch error, never as a hung GPU
+        if (!done && ++spins > (1u << 26)) __trap();
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;  // descriptor version (Blackwell)
+    d |= 2ull << 61;  // SWIZZLE_128B
+    return d;
+}
+// tcgen05 instruction descriptor: D fp32, A/B tf32, dense (cute::UMMA::InstrDescriptor bit layout).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct TcCfg {
+    static constexpr int kStageBytes = 2 * (kTcBM + BN) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
+    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;       // two accumulator stages (power of two)
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
+};
+
+// One kernel for the three operand-major combinations. A_MN / B_MN: operand is MN-major (reduction index slow).
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const TcShape sh, const TcEpilogue ep) {
+    using Cfg = TcCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t kABytes = kTcBM * kTcBK * 4;   // one of A_hi / A_lo
+    constexpr uint32_t kBBytes = BN * kTcBK * 4;
+    constexpr uint32_t kBoxBytes = 32 * kTcBK * 4;    // one MN-major box: 32 k-rows x 128 B
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024 B alignment
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    const uint32_t tmem_slot = bar_base + (2 * kStages + 4) * 8;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = sh.num_m_blocks * sh.num_n_blocks;
+    const int total_work = tiles * sh.num_splits;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tmem_full_bar(s), 1);
+            mbar_init(tmem_empty_bar(s), 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int tile = w % tiles, split = w / tiles;
+                const int m0 = (tile / sh.num_n_blocks) * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
+                const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t bar = full_bar(stage);
+                    mbar_expect_tx(bar, Cfg::kStageBytes);
+                    const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
+                    const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
+                    const int k0 = kb * kTcBK;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(a_hi, &map_a_hi, bar, k0, m0);
+                        tma_load_2d(a_lo, &map_a_lo, bar, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kTcBM / 32; j++) {
+                            tma_load_2d(a_hi + j * kBoxBytes, &map_a_hi, bar, m0 + j * 32, k0);
+                            tma_load_2d(a_lo + j * kBoxBytes, &map_a_lo, bar, m0 + j * 32, k0);
+                        }
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(b_hi, &map_b_hi, bar, k0, n0);
+                        tma_load_2d(b_lo, &map_b_lo, bar, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; j++) {
+                            tma_load_2d(b_hi + j * kBoxBytes, &map_b_hi, bar, n0 + j * 32, k0);
+                            tma_load_2d(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * 32, k0);
+                        }
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTcBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // K-major: a k-slice of 8 fp32 is 32 bytes inside the 128-byte swizzled row; 8-row groups are 1024 B apart.
+            // MN-major: a k-slice is 8 rows of 128 B (1024 B); 32-wide MN blocks are one box (4096 B) apart.
+            constexpr uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+            constexpr uint32_t a_lbo = A_MN ? kBoxBytes : 0u, b_lbo = B_MN ? kBoxBytes : 0u;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w / tiles;
+                const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
+                    const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+                    for (int ks = 0; ks < kTcBK / 8; ks++) {
+                        const uint64_t da_hi = umma_desc(a_hi + ks * a_step, a_lbo, 1024);
+                        const uint64_t da_lo = umma_desc(a_lo + ks * a_step, a_lbo, 1024);
+                        const uint64_t db_hi = umma_desc(b_hi + ks * b_step, b_lbo, 1024);
+                        const uint64_t db_lo = umma_desc(b_lo + ks * b_step, b_lbo, 1024);
+                        tc_mma_tf32(tmem_d, da_hi, db_hi, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+                        tc_mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full_bar(acc));    // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int tile = w % tiles, split = w / tiles;
+            const int m0 = (tile / sh.num_n_blocks) * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < sh.m;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= sh.n) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                tmem_ld_wait();
+                if (c == BN / 32 - 1 || col0 + 32 >= sh.n) {  // last TMEM read of this tile: release the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                }
+                if (!row_ok) continue;
+                float x[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    float t = __uint_as_float(v[i]);
+                    const int col = col0 + i;
+                    if (col < sh.n) {
+                        if (ep.bias) t += __ldg(ep.bias + col);
+                        if (ep.relu) t = fmaxf(t, 0.f);
+                        if (ep.mask) t = __ldg(ep.mask + (size_t)row * ep.ldmask + col) > 0.f ? t : 0.f;
+                    }
+                    x[i] = t;
+                }
+                const bool full = col0 + 32 <= sh.n;
+                if (cplain) {
+                    if (ep.transpose_out) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (col0 + i < sh.n) cplain[(size_t)(col0 + i) * ep.ldc + row] = x[i];
+                    } else {
+                        float* dst = cplain + (size_t)row * ep.ldc + col0;
+                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i++)
+                                if (col0 + i < sh.n) dst[i] = x[i];
+                        }
+                    }
+                }
+                if (ep.c_hi) {
+                    float* dh = ep.c_hi + (size_t)row * ep.ldc_split + col0;
+                    float* dl = ep.c_lo + (size_t)row * ep.ldc_split + col0;
+                    float h[32], l[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        h[i] = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+                        l[i] = x[i] - h[i];
+                    }
+                    if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            *reinterpret_cast<float4*>(dh + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+                            *reinterpret_cast<float4*>(dl + i) = make_float4(l[i], l[i + 1], l[i + 2], l[i + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (col0 + i < sh.n) { dh[i] = h[i]; dl[i] = l[i]; }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    }
+}
+
+// fp32 -> (hi, lo) split of a [rows, cols] matrix (row stride ld_in) into two dense [rows, ld_out] arrays;
+// columns [cols, ld_out) are zero-filled. Algorithmic traffic 12 B per element.
+__global__ void split_tf32_kernel(const float* __restrict__ x, int ld_in, size_t rows, int cols, int ld_out,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+    const size_t total = rows * (size_t)ld_out;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        float v = 0.f;
+        if (c < cols) v = __ldg(x + r * ld_in + c);
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st) {
+    if (rows == 0 || ld_out == 0) return FI_OK;
+    const size_t total = rows * (size_t)ld_out;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    LaunchScope ls("split_tf32_kernel", st, 4.0 * (double)rows * cols + 8.0 * (double)total, kWorkBytes);
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, ld_out, hi, lo);
+    return ls.done();
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    });
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row stride ld elements;
+// box = 32 inner elements (128 B, the swizzle span) x box_outer rows. Out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16)
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM: operand base / row stride must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FI_OK;
+}
+
+static int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32)); }
+
+static int tc_splits(int trans, int m, int n, int k) {
+    if (trans != 2) return 1;
+    const int bn = pick_bn(n);
+    const int tiles = ((m + kTcBM - 1) / kTcBM) * ((n + bn - 1) / bn);
+    const int num_kb = (k + kTcBK - 1) / kTcBK;
+    int s = kNumSMs / tiles;           // all CTAs of one wave; CTAs of the same split share operand rows in L2
+    if (s > num_kb / 4) s = num_kb / 4;  // at least 4 k-blocks per split
+    return s < 1 ? 1 : s;
+}
+
+size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k) {
+    const int s = tc_splits(trans, m, n, k);
+    return s > 1 ? (size_t)s * m * n * sizeof(float) : 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEpilogue& ep, int grid, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    LaunchScope ls("gemm_tc_kernel", st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
+    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], sh, ep);
+    return ls.done();
+}
+
+// C = op(A) op(B) with pre-split operands. trans as in launch_gemm: 0 "NT" A[m,k] B[n,k]; 1 "NN" A[m,k] B[k,n];
+// 2 "TN" A[k,m] B[k,n] (split-K through `workspace`, reduced into out.c; no epilogue ops).
+int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,
+                         const float* mask, int ldmask, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (m <= 0 || n <= 0 || k <= 0) return FI_OK;
+    if (trans < 0 || trans > 2) return set_error(FI_ERR_ARG, "gemm: trans must be 0, 1 or 2");
+    if (!a.hi || !a.lo || !b.hi || !b.lo || (!out.c && !out.c_hi)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: null operand");
+    const bool a_mn = trans == 2, b_mn = trans != 0;
+    const int bn = pick_bn(n);
+    TcShape sh;
+    sh.m = m; sh.n = n; sh.k = k;
+    sh.num_m_blocks = (m + kTcBM - 1) / kTcBM;
+    sh.num_n_blocks = (n + bn - 1) / bn;
+    sh.num_kb = (k + kTcBK - 1) / kTcBK;
+    sh.num_splits = tc_splits(trans, m, n, k);
+    TcEpilogue ep;
+    ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
+    ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
+    if (sh.num_splits > 1) {
+        const size_t need = (size_t)sh.num_splits * m * n * sizeof(float);
+        if (!workspace || workspace_bytes < need || bias || relu || mask || out.c_hi || !out.c) {
+            sh.num_splits = 1;  // no room for partials (or an epilogue is requested): one split per tile
+        } else {
+            ep.c = static_cast<float*>(workspace);
+            ep.split_stride = (size_t)m * n;
+            if (out.transpose ? out.ldc != m : out.ldc != n)
+                return set_error(FI_ERR_ARG, "tcgen05 GEMM: split-K needs a dense output (ldc=%d)", out.ldc);
+        }
+    }
+    sh.kb_per_split = (sh.num_kb + sh.num_splits - 1) / sh.num_splits;
+    sh.num_splits = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;
+    CUtensorMap maps[4];
+    if (!a_mn) {
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM));
+    } else {
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK));
+    }
+    if (!b_mn) {
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn));
+    } else {
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK));
+    }
+    const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    int rc;
+#define FI_TC(BNV)                                                                                    \
+    (trans == 0 ? launch_variant<BNV, false, false>(maps, sh, ep, grid, st)                           \
+                : trans == 1 ? launch_variant<BNV, false, true>(maps, sh, ep, grid, st)               \
+                             : launch_variant<BNV, true, true>(maps, sh, ep, grid, st))
+    if (bn == 256) rc = FI_TC(256);
+    else if (bn == 128) rc = FI_TC(128);
+    else if (bn == 64) rc = FI_TC(64);
+    else rc = FI_TC(32);
+#undef FI_TC
+    FI_TRY(rc);
+    if (sh.num_splits > 1) {
+        const size_t total_out = (size_t)m * n;
+        FI_TRY(launch_reduce_splits(static_cast<const float*>(workspace), sh.num_splits, total_out, total_out, out.c, st));
+    }
+    return FI_OK;
+}
+
+bool gemm_tc_available() { return encode_fn() != nullptr; }
+
+// ---- plain fp32 entry (fi_op_gemm, FarmerLstm dense stack): split the operands into the workspace first --------
+static size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool gemm_tc_supported(int trans, int m, int n, int k, const float*, int, const float*, int, const float*, int) {
+    // tiny problems are launch-latency bound either way; the tensor-core path needs one full k-block
+    return trans >= 0 && trans <= 2 && m >= 1 && n >= 1 && k >= 1 && encode_fn() != nullptr;
+}
+
+size_t gemm_tc_workspace_bytes(int trans, int m, int n, int k) {
+    const size_t a_rows = trans == 2 ? k : m, a_cols = trans == 2 ? m : k;
+    const size_t b_rows = trans == 0 ? n : k, b_cols = trans == 0 ? k : n;
+    return 2 * align256(a_rows * pad4(a_cols) * 4) + 2 * align256(b_rows * pad4(b_cols) * 4) +
+           align256(gemm_tc_split_workspace_bytes(trans, m, n, k));
+}
+
+int launch_gemm_tc(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc,
+                   const float* bias, int relu, const float* mask, int ldmask, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
+    if (m <= 0 || n <= 0) return FI_OK;
+    if (workspace_bytes < gemm_tc_workspace_bytes(trans, m, n, k) || !workspace)
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM: workspace too small (need %zu bytes)", gemm_tc_workspace_bytes(trans, m, n, k));
+    const size_t a_rows = trans == 2 ? k : m, a_cols = trans == 2 ? m : k;
+    const size_t b_rows = trans == 0 ? n : k, b_cols = trans == 0 ? k : n;
+    const size_t a_ld = pad4(a_cols), b_ld = pad4(b_cols);
+    char* ws = static_cast<char*>(workspace);
+    float* a_hi = reinterpret_cast<float*>(ws); ws += align256(a_rows * a_ld * 4);
+    float* a_lo = reinterpret_cast<float*>(ws); ws += align256(a_rows * a_ld * 4);
+    float* b_hi = reinterpret_cast<float*>(ws); ws += align256(b_rows * b_ld * 4);
+    float* b_lo = reinterpret_cast<float*>(ws); ws += align256(b_rows * b_ld * 4);
+    FI_TRY(launch_split_tf32(a, lda, a_rows, (int)a_cols, (int)a_ld, a_hi, a_lo, st));
+    FI_TRY(launch_split_tf32(b, ldb, b_rows, (int)b_cols, (int)b_ld, b_hi, b_lo, st));
+    SplitMat sa{a_hi, a_lo, (int)a_ld}, sb{b_hi, b_lo, (int)b_ld};
+    TcOut out{c, ldc, nullptr, nullptr, 0, 0};
+    const size_t split_ws = gemm_tc_split_workspace_bytes(trans, m, n, k);
+    if (trans == 2 && ldc != n) {  // split-K partials need a dense output
+        return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, nullptr, 0, st);
+    }
+    return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, split_ws ? ws : nullptr, split_ws, st);
+}
+
 }  // namespace fi

@@ -101,8 +101,13 @@ class AdamParity:
       * teacher-forced: a float64 oracle that is fed the CUDA gradients each step must end with the
         same parameters, ALL elements, relative L2 <= 1e-5 (the gradients themselves are compared at
         1e-5 against the oracle's own at every step, at the same parameters);
-      * free-running: an independent float64 oracle; relative L2 <= 1e-5 over all but the 0.5 % worst
-        elements (the sign-flip candidates), and <= 1e-3 over everything (bounded update 2*lr/step).
+      * free-running: an independent float64 oracle that never sees CUDA data. It cannot be held to 1e-5:
+        besides the sign(g) effect, a ReLU unit whose pre-activation is within fp32 rounding of zero is
+        decided differently by fp32 and float64 (a handful per step at 64 x 100), which moves whole
+        weight-gradient rows of the layers below by ~1e-4 relative (measured; tools/diag_ac.py), and Adam
+        turns that into parameter differences of the same order. It is kept as a sanity bound: relative
+        L2 <= 5e-4 over the 99.5 % best elements and <= 1e-3 over everything (libtorch's own fp32 step
+        shows the same effect against float64).
     """
 
     def __init__(self, forced, free):
@@ -118,7 +123,7 @@ class AdamParity:
         e_forced = rel_l2(cuda_params, self.forced.params())
         assert e_forced < tol, f"teacher-forced parameters differ: rel l2 {e_forced:.3e}"
         e_trim = trimmed_rel_l2(cuda_params, self.free.params())
-        assert e_trim < tol, f"free-running parameters differ (99.5 % best): rel l2 {e_trim:.3e}"
+        assert e_trim < 5e-4, f"free-running parameters differ (99.5 % best): rel l2 {e_trim:.3e}"
         e_all = rel_l2(cuda_params, self.free.params())
         assert e_all < 1e-3, f"free-running parameters differ: rel l2 {e_all:.3e}"
         return e_forced, e_trim, e_all

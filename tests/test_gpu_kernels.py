@@ -289,10 +289,12 @@ def test_vtrace_loss_head_vs_oracle(fi, oracle, torch_cuda, m, t):
 GEMM_CASES = [("NT", 640, 512, 162, 256), ("NT", 6400, 512, 512, 512), ("NT", 100, 17, 512, 512), ("NT", 64, 1, 512, 512),
               ("NN", 640, 512, 17, 17), ("NN", 1000, 512, 512, 512), ("NN", 64, 612, 512, 512),
               ("TN", 512, 162, 6400, 512), ("TN", 512, 512, 6400, 512), ("TN", 17, 512, 3000, 17), ("TN", 512, 612, 64, 512),
-              ("NT", 1, 1, 1, 1), ("NT", 129, 130, 19, 19)]
+              ("NT", 1, 1, 1, 1), ("NT", 129, 130, 19, 19),
+              ("NT", 4096, 512, 512, 512), ("NN", 2048, 512, 512, 512), ("TN", 512, 512, 20000, 512), ("TN", 512, 162, 3333, 512),
+              ("NT", 300, 100, 70, 72), ("NN", 260, 40, 33, 36), ("TN", 130, 60, 77, 132)]
 
 
-@pytest.mark.parametrize("mode", ["simt", "auto"])
+@pytest.mark.parametrize("mode", ["simt", "tcgen05"])
 @pytest.mark.parametrize("trans,m,n,k,lda", GEMM_CASES)
 def test_gemm_fp32_accuracy(fi, torch_cuda, trans, m, n, k, lda, mode):
     """C = op(A) op(B) (+bias, ReLU) within fp32 rounding of the float64 product: the learner's
