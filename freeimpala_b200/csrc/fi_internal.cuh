@@ -13,7 +13,8 @@ int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount
                        float lambda_, float* vs, float* pg_adv, cudaStream_t stream);
 int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar, float c_bar,
                             float pg_rho_bar, float lambda_, float baseline_cost, float entropy_cost, float* dhead,
-                            float* vs, float* pg_adv, double* losses, cudaStream_t stream);
+                            float* vs, float* pg_adv, double* losses, cudaStream_t stream,
+                            float* dhead_hi = nullptr, float* dhead_lo = nullptr, int ld_split = 0);
 
 // trans: 0 "NT" C = A[m,k] B[n,k]^T; 1 "NN" C = A[m,k] B[k,n]; 2 "TN" C = A[k,m]^T B[k,n].
 int launch_gemm_simt(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c,
@@ -22,6 +23,8 @@ int launch_gemm_simt(int trans, int m, int n, int k, const float* a, int lda, co
 size_t gemm_simt_workspace_bytes(int trans, int m, int n, int k);
 int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);
+int launch_colsum2(const float* x, const float* x2, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
 size_t colsum_workspace_bytes(int m, int n);
 
 // out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).

@@ -230,7 +230,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partial, int spli
 
 // Column sums of dY[m, n] (bias gradient): partial[z][j] = sum over a row range, then reduced.
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ x, int ldx, int m, int n, int rows_per_block,
+colsum_partial_kernel(const float* __restrict__ x, const float* __restrict__ x2, int ldx, int m, int n, int rows_per_block,
                       float* __restrict__ partial) {
     // block handles rows [r0, r1) and 32 columns (blockIdx.x); 8 row-lanes x 32 column-lanes
     __shared__ float red[8][33];
@@ -239,7 +239,10 @@ colsum_partial_kernel(const float* __restrict__ x, int ldx, int m, int n, int ro
     const int r0 = blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
     float s = 0.f;
     if (col < n)
-        for (int r = r0 + ry; r < r1; r += 8) s += __ldg(x + (size_t)r * ldx + col);
+        for (int r = r0 + ry; r < r1; r += 8) {
+            s += __ldg(x + (size_t)r * ldx + col);
+            if (x2) s += __ldg(x2 + (size_t)r * ldx + col);  // hi/lo pair: the column sum of hi + lo
+        }
     red[ry][cx] = s;
     __syncthreads();
     if (ry == 0 && col < n) {
@@ -333,6 +336,10 @@ size_t colsum_workspace_bytes(int m, int n) {
 }
 int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream) {
+    return launch_colsum2(x, nullptr, ldx, m, n, out, workspace, workspace_bytes, stream);
+}
+int launch_colsum2(const float* x, const float* x2, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
     if (n <= 0) return FI_OK;
     int rb = (m + 511) / 512;
     if (rb > 512) rb = 512;
@@ -340,8 +347,8 @@ int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* works
     const int rows_per_block = (m + rb - 1) / rb;
     if (!workspace || workspace_bytes < (size_t)rb * n * sizeof(float)) return set_error(FI_ERR_ARG, "colsum: workspace too small");
     dim3 grid((n + 31) / 32, rb);
-    LaunchScope lc("colsum_partial_kernel", stream, 4.0 * (double)m * n, kWorkBytes);
-    colsum_partial_kernel<<<grid, 256, 0, stream>>>(x, ldx, m, n, rows_per_block, (float*)workspace);
+    LaunchScope lc("colsum_partial_kernel", stream, (x2 ? 8.0 : 4.0) * (double)m * n, kWorkBytes);
+    colsum_partial_kernel<<<grid, 256, 0, stream>>>(x, x2, ldx, m, n, rows_per_block, (float*)workspace);
     FI_TRY(lc.done());
     LaunchScope lr("reduce_splits_kernel", stream, 4.0 * (double)n * (rb + 1), kWorkBytes);
     reduce_splits_kernel<<<(n + 255) / 256, 256, 0, stream>>>((const float*)workspace, rb, (size_t)n, (size_t)n, out);

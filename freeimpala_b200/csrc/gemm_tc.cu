@@ -4,21 +4,29 @@
 // TF32 / bf16 operands, so every fp32 operand x is carried as an exact pair
 //     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
 //                    lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits),
-// and each product is issued as three kind::tf32 MMAs into the same fp32 TMEM accumulator:
-//     D += A_hi B_hi + A_hi B_lo + A_lo B_hi        (the dropped A_lo B_lo term is ~2^-22 relative).
+// and each product is issued as three kind::tf32 MMAs:
+//     main += A_hi B_hi            corr += A_hi B_lo + A_lo B_hi      (A_lo B_lo ~ 2^-22 relative is dropped).
+// Measured on B200: the tensor core adds into its fp32 accumulator with truncation, ~1 ulp of the
+// running sum per MMA, biased towards zero (error grew linearly with K: 2.4e-5 at K=32, 4.6e-4 at K=512
+// on sums of magnitude ~20). The big products therefore accumulate in TMEM only over a CHUNK of 4
+// k-blocks (16 MMAs); the promotion warps then add the chunk to fp32 register accumulators with
+// round-to-nearest (the scheme of Ootomo & Yokota 2022, at chunk granularity). The correction
+// terms are 2^-11 smaller, so their own truncation is harmless and they stay in TMEM per tile.
 //
 // Kernel anatomy (one CTA per SM, persistent over output tiles; 256 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A_hi, A_lo, B_hi, B_lo into a
 //              multi-stage shared-memory ring, completion on mbarriers;
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=8) x 4 k-slices x 3 products
-//              per 32-wide k-block, tcgen05.commit releases the stage / publishes the accumulator;
-//   warp 2     TMEM allocator (2 accumulator stages of BN fp32 columns, so the epilogue of tile i overlaps the
-//              MMAs of tile i+1);
-//   warps 4-7  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / ReLU-mask, then either a plain
-//              fp32 store or the hi/lo split store that feeds the next GEMM.
-// Operand layouts (UMMA "major"): K-major tiles are [rows][32 k] with one 128-byte row per matrix row;
-// MN-major tiles are [32 k][32 mn] boxes (the reduction index is the slow one), so dgrad (B = W[n,k] read along
-// n) and wgrad (both operands read along the batch rows) need no transposed copies.
+//              per 32-wide k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
+//   warp 2     TMEM allocator: 2 chunk accumulators + 2 correction accumulators of BN fp32 columns each, so the
+//              promotion of chunk i overlaps the MMAs of chunk i+1 and the epilogue of tile j those of tile j+1;
+//   warps 4-7  promotion + epilogue: tcgen05.ld (32 lanes x 32 columns per warp) into BN register accumulators per
+//              thread, then bias / ReLU / ReLU-mask and either a plain fp32 store or the hi/lo split store that
+//              feeds the next GEMM.
+// Operand layouts (UMMA "major"): K-major tiles are [rows][32 k] with one 128-byte row per matrix row (128B
+// swizzle, 16-byte atoms); MN-major tiles are [32 k][32 mn] boxes (the reduction index is the slow one; tf32 only
+// supports the 128B swizzle with 32-byte atoms there), so dgrad (B = W[n,k] read along n) and wgrad (both operands
+// read along the batch rows) need no transposed copies.
 #include <cuda.h>
 
 #include <mutex>
@@ -30,6 +38,7 @@ namespace fi {
 constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int kTcThreads = 256;
+constexpr int kTcChunk = 4;      // k-blocks accumulated in TMEM before promotion to registers (16 main MMAs)
 constexpr int kTcSmemLimit = 227 * 1024;
 
 struct TcEpilogue {
@@ -111,13 +120,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;  // descriptor version (Blackwell)
-    d |= 2ull << 61;  // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms)
     return d;
 }
 // tcgen05 instruction descriptor: D fp32, A/B tf32, dense (cute::UMMA::InstrDescriptor bit layout).
@@ -129,8 +138,9 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, 
 template <int BN>
 struct TcCfg {
     static constexpr int kStageBytes = 2 * (kTcBM + BN) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
-    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
-    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;       // two accumulator stages (power of two)
+    static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
+    static constexpr int kStages = BN >= 128 ? 3 : 4;
+    static constexpr int kTmemCols = 4 * BN;                          // main[2] + corr[2] (a power of two >= 32)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
 };
@@ -147,13 +157,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     constexpr uint32_t kBBytes = BN * kTcBK * 4;
     constexpr uint32_t kBoxBytes = 32 * kTcBK * 4;    // one MN-major box: 32 k-rows x 128 B
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024 B alignment
-    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
-    const uint32_t tmem_slot = bar_base + (2 * kStages + 4) * 8;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
+    // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2], corr_empty[2]
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    const uint32_t tmem_slot = bar_base + (2 * kStages + 6) * 8;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    auto main_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto main_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    auto corr_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 4 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = sh.num_m_blocks * sh.num_n_blocks;
@@ -165,8 +177,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; s++) {
-            mbar_init(tmem_full_bar(s), 1);
-            mbar_init(tmem_empty_bar(s), 4);  // one arrival per epilogue warp
+            mbar_init(main_full_bar(s), 1);
+            mbar_init(main_empty_bar(s), 4);  // one arrival per promotion warp
+            mbar_init(corr_empty_bar(s), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -180,6 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    // TMEM columns: main chunk accumulators at [0, BN) and [BN, 2BN); correction accumulators at [2BN, 3BN), [3BN, 4BN)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -225,119 +239,155 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kTcBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-            // K-major: a k-slice of 8 fp32 is 32 bytes inside the 128-byte swizzled row; 8-row groups are 1024 B apart.
-            // MN-major: a k-slice is 8 rows of 128 B (1024 B); 32-wide MN blocks are one box (4096 B) apart.
+            // K-major (128B swizzle, 16 B atoms): a k-slice of 8 fp32 is 32 bytes inside the 128-byte row; 8-row groups
+            // are 1024 B apart (SBO). MN-major (128B swizzle, 32 B atoms): a k-slice is 8 rows of 128 B = two 4-row
+            // atoms 512 B apart (SBO); 32-wide MN blocks are one TMA box (4096 B) apart (LBO).
             constexpr uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
             constexpr uint32_t a_lbo = A_MN ? kBoxBytes : 0u, b_lbo = B_MN ? kBoxBytes : 0u;
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
+            constexpr uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+            constexpr uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
+            int stage = 0, mb = 0, cb = 0;
+            uint32_t phase = 0, mphase = 0, cphase = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
-                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = kb0; kb < kb1; kb++) {
-                    mbar_wait(full_bar(stage), phase);
+                mbar_wait(corr_empty_bar(cb), cphase ^ 1);
+                const uint32_t tmem_corr = tmem_base + (uint32_t)((2 + cb) * BN);
+                for (int kc = kb0; kc < kb1; kc += kTcChunk) {
+                    mbar_wait(main_empty_bar(mb), mphase ^ 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
-                    const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
+                    const uint32_t tmem_main = tmem_base + (uint32_t)(mb * BN);
+                    const int kce = min(kb1, kc + kTcChunk);
+                    for (int kb = kc; kb < kce; kb++) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
+                        const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kTcBK / 8; ks++) {
-                        const uint64_t da_hi = umma_desc(a_hi + ks * a_step, a_lbo, 1024);
-                        const uint64_t da_lo = umma_desc(a_lo + ks * a_step, a_lbo, 1024);
-                        const uint64_t db_hi = umma_desc(b_hi + ks * b_step, b_lbo, 1024);
-                        const uint64_t db_lo = umma_desc(b_lo + ks * b_step, b_lbo, 1024);
-                        tc_mma_tf32(tmem_d, da_hi, db_hi, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-                        tc_mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
-                        tc_mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+                        for (int ks = 0; ks < kTcBK / 8; ks++) {
+                            const uint64_t da_hi = umma_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+                            const uint64_t da_lo = umma_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+                            const uint64_t db_hi = umma_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+                            const uint64_t db_lo = umma_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+                            tc_mma_tf32(tmem_main, da_hi, db_hi, idesc, (kb > kc || ks > 0) ? 1u : 0u);
+                            tc_mma_tf32(tmem_corr, da_hi, db_lo, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                            tc_mma_tf32(tmem_corr, da_lo, db_hi, idesc, 1u);
+                        }
+                        tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    tc_commit(main_full_bar(mb));     // chunk complete (and, for the last chunk, the tile's corrections)
+                    if (++mb == 2) { mb = 0; mphase ^= 1; }
                 }
-                tc_commit(tmem_full_bar(acc));    // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++cb == 2) { cb = 0; cphase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== promotion + epilogue =====================
         const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        int mb = 0, cb = 0;
+        uint32_t mphase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int tile = w % tiles, split = w / tiles;
             const int m0 = (tile / sh.num_n_blocks) * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
+            const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < sh.m;
-            mbar_wait(tmem_full_bar(acc), acc_phase);
-            tc_fence_after();
+            float acc[BN];
+#pragma unroll
+            for (int i = 0; i < BN; i++) acc[i] = 0.f;
+            for (int kc = kb0; kc < kb1; kc += kTcChunk) {
+                mbar_wait(main_full_bar(mb), mphase);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * BN + c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[c * 32 + i] += __uint_as_float(v[i]);  // round-to-nearest promotion
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(main_empty_bar(mb));
+                if (++mb == 2) { mb = 0; mphase ^= 1; }
+            }
+            // the last chunk's commit also covers this tile's correction MMAs
+#pragma unroll
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)((2 + cb) * BN + c * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[c * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(corr_empty_bar(cb));
+            cb ^= 1;
+            if (!row_ok) continue;
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < BN / 32; c++) {
                 const int col0 = n0 + c * 32;
-                if (col0 >= sh.n) break;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                tmem_ld_wait();
-                if (c == BN / 32 - 1 || col0 + 32 >= sh.n) {  // last TMEM read of this tile: release the accumulator
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-                }
-                if (!row_ok) continue;
-                float x[32];
+                if (col0 < sh.n) {
+                    float x[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    float t = __uint_as_float(v[i]);
-                    const int col = col0 + i;
-                    if (col < sh.n) {
-                        if (ep.bias) t += __ldg(ep.bias + col);
-                        if (ep.relu) t = fmaxf(t, 0.f);
-                        if (ep.mask) t = __ldg(ep.mask + (size_t)row * ep.ldmask + col) > 0.f ? t : 0.f;
+                    for (int i = 0; i < 32; i++) {
+                        float t = acc[c * 32 + i];
+                        const int col = col0 + i;
+                        if (col < sh.n) {
+                            if (ep.bias) t += __ldg(ep.bias + col);
+                            if (ep.relu) t = fmaxf(t, 0.f);
+                            if (ep.mask) t = __ldg(ep.mask + (size_t)row * ep.ldmask + col) > 0.f ? t : 0.f;
+                        }
+                        x[i] = t;
                     }
-                    x[i] = t;
-                }
-                const bool full = col0 + 32 <= sh.n;
-                if (cplain) {
-                    if (ep.transpose_out) {
+                    const bool full = col0 + 32 <= sh.n;
+                    if (cplain) {
+                        if (ep.transpose_out) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            if (col0 + i < sh.n) cplain[(size_t)(col0 + i) * ep.ldc + row] = x[i];
-                    } else {
-                        float* dst = cplain + (size_t)row * ep.ldc + col0;
-                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                            for (int i = 0; i < 32; i++)
+                                if (col0 + i < sh.n) cplain[(size_t)(col0 + i) * ep.ldc + row] = x[i];
+                        } else {
+                            float* dst = cplain + (size_t)row * ep.ldc + col0;
+                            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; i++)
+                                    if (col0 + i < sh.n) dst[i] = x[i];
+                            }
+                        }
+                    }
+                    if (ep.c_hi) {
+                        float* dh = ep.c_hi + (size_t)row * ep.ldc_split + col0;
+                        float* dl = ep.c_lo + (size_t)row * ep.ldc_split + col0;
+                        if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 h, l;
+                                h.x = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u); l.x = x[i] - h.x;
+                                h.y = __uint_as_float(__float_as_uint(x[i + 1]) & 0xFFFFE000u); l.y = x[i + 1] - h.y;
+                                h.z = __uint_as_float(__float_as_uint(x[i + 2]) & 0xFFFFE000u); l.z = x[i + 2] - h.z;
+                                h.w = __uint_as_float(__float_as_uint(x[i + 3]) & 0xFFFFE000u); l.w = x[i + 3] - h.w;
+                                *reinterpret_cast<float4*>(dh + i) = h;
+                                *reinterpret_cast<float4*>(dl + i) = l;
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; i++)
-                                if (col0 + i < sh.n) dst[i] = x[i];
+                                if (col0 + i < sh.n) {
+                                    const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+                                    dh[i] = h;
+                                    dl[i] = x[i] - h;
+                                }
                         }
-                    }
-                }
-                if (ep.c_hi) {
-                    float* dh = ep.c_hi + (size_t)row * ep.ldc_split + col0;
-                    float* dl = ep.c_lo + (size_t)row * ep.ldc_split + col0;
-                    float h[32], l[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        h[i] = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
-                        l[i] = x[i] - h[i];
-                    }
-                    if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            *reinterpret_cast<float4*>(dh + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-                            *reinterpret_cast<float4*>(dl + i) = make_float4(l[i], l[i + 1], l[i + 2], l[i + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            if (col0 + i < sh.n) { dh[i] = h[i]; dl[i] = l[i]; }
                     }
                 }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -396,7 +446,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row stride ld elements;
 // box = 32 inner elements (128 B, the swizzle span) x box_outer rows. Out-of-bounds elements read as zero.
-static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                    bool mn_major) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16)
@@ -406,13 +457,14 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_
     cuuint32_t box[2] = {32, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FI_OK;
 }
 
-static int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32)); }
+static int pick_bn(int n) { return n > 64 ? 128 : (n > 32 ? 64 : 32); }
 
 static int tc_splits(int trans, int m, int n, int k) {
     if (trans != 2) return 1;
@@ -475,18 +527,18 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     sh.num_splits = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;
     CUtensorMap maps[4];
     if (!a_mn) {
-        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM));
-        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM));
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
     } else {
-        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK));
-        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK));
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK, true));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK, true));
     }
     if (!b_mn) {
-        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn));
-        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn));
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn, false));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn, false));
     } else {
-        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK));
-        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK));
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
     }
     const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
@@ -495,8 +547,7 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     (trans == 0 ? launch_variant<BNV, false, false>(maps, sh, ep, grid, st)                           \
                 : trans == 1 ? launch_variant<BNV, false, true>(maps, sh, ep, grid, st)               \
                              : launch_variant<BNV, true, true>(maps, sh, ep, grid, st))
-    if (bn == 256) rc = FI_TC(256);
-    else if (bn == 128) rc = FI_TC(128);
+    if (bn == 128) rc = FI_TC(128);
     else if (bn == 64) rc = FI_TC(64);
     else rc = FI_TC(32);
 #undef FI_TC

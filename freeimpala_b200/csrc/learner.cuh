@@ -69,6 +69,7 @@ struct Player {
     void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;
     void* colsum_ws = nullptr; size_t colsum_ws_bytes = 0;
     void* model_ws = nullptr;
+    void* ac_tc = nullptr;          // AcTc (model_ac.cu): hi/lo activation pairs of the tensor-core path
     void* farmer_ws = nullptr;      // FarmerWs (model_farmer.cu): training workspaces
     void* farmer_inf_ws = nullptr;  // FarmerWs for batched inference
     unsigned char* stage_dev = nullptr;  // staged batch (fi_learner_stage_batch)

@@ -2,32 +2,80 @@
 // Trunk = the reference's dense1..5 shapes (cmd/libtorch_bench/main.cpp:17-21) applied per
 // transition to the 162-feature observation; one fused head [17, 512]: 16 policy logits + value.
 // Parameter order: dense1.w [512,162], dense1.b, dense2..5 .w [512,512], .b, head.w [17,512], head.b.
-// The first GEMM reads the observations straight out of the gathered batch (row stride 256
-// words = one 1024-byte record): no decode pass, no copy.
+//
+// Two execution paths, same math:
+//  * tensor-core path (gemm_mode auto / tcgen05): every GEMM is the tcgen05 3xTF32 kernel (gemm_tc.cu).
+//    Activations and back-propagated gradients live in HBM as exact hi/lo pairs written by the
+//    producing GEMM's epilogue, so no GEMM ever re-splits its big operand; only the observations
+//    (read out of the gathered batch, row stride 256 words) and the weights are split by a pre-pass.
+//  * SIMT path (gemm_mode simt): fp32 FFMA GEMMs (gemm_simt.cu); the first GEMM reads the
+//    observations straight out of the gathered batch.
 #include "learner.cuh"
 
 namespace fi {
 
+constexpr int kObsLd = 164;     // 162 observation words padded to a 16-byte multiple (TMA row stride)
+constexpr int kDheadLd = 32;    // 17 head gradients padded to one k-block
+
+struct AcTc {  // tensor-core path state, owned by the Player (Player::ac_tc)
+    float *w_hi = nullptr, *w_lo = nullptr;        // split parameter arena (same offsets as params)
+    float *w1_hi = nullptr, *w1_lo = nullptr;      // dense1.w re-laid out as [512, 164]
+    float *obs_hi = nullptr, *obs_lo = nullptr;    // [rows, 164]
+    float* act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* d_hi[2] = {nullptr, nullptr};
+    float* d_lo[2] = {nullptr, nullptr};
+    float *dhead_hi = nullptr, *dhead_lo = nullptr;  // [rows, 32], columns 17..31 stay zero
+    void* ws = nullptr; size_t ws_bytes = 0;         // split-K partials
+};
+
+static bool use_tc(const fi_learner* l) { return l->cfg.gemm_mode != FI_GEMM_SIMT && gemm_tc_available(); }
+
 int ac_alloc(fi_learner* l, Player* p) {
     const size_t rows = l->cfg.batch_size * l->cfg.entry_size;
+    if (l->cfg.gemm_mode == FI_GEMM_TCGEN05 && !gemm_tc_available())
+        return set_error(FI_ERR_STATE, "gemm_mode tcgen05 requested but cuTensorMapEncodeTiled is unavailable");
+    FI_CUDA_OK(cudaMalloc((void**)&p->head, rows * kHead * sizeof(float)));
+    p->colsum_ws_bytes = colsum_workspace_bytes((int)rows, kHid);
+    FI_CUDA_OK(cudaMalloc(&p->colsum_ws, p->colsum_ws_bytes));
+    if (use_tc(l)) {
+        AcTc* t = new AcTc();
+        p->ac_tc = t;
+        const size_t ab = l->arena_elems * sizeof(float), rb = rows * kHid * sizeof(float);
+        FI_CUDA_OK(cudaMalloc((void**)&t->w_hi, ab));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w_lo, ab));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_hi, (size_t)kHid * kObsLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_lo, (size_t)kHid * kObsLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_hi, rows * kObsLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_lo, rows * kObsLd * sizeof(float)));
+        for (int i = 0; i < 5; i++) {
+            FI_CUDA_OK(cudaMalloc((void**)&t->act_hi[i], rb));
+            FI_CUDA_OK(cudaMalloc((void**)&t->act_lo[i], rb));
+        }
+        for (int i = 0; i < 2; i++) {
+            FI_CUDA_OK(cudaMalloc((void**)&t->d_hi[i], rb));
+            FI_CUDA_OK(cudaMalloc((void**)&t->d_lo[i], rb));
+        }
+        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_hi, rows * kDheadLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_lo, rows * kDheadLd * sizeof(float)));
+        FI_CUDA_OK(cudaMemset(t->dhead_hi, 0, rows * kDheadLd * sizeof(float)));
+        FI_CUDA_OK(cudaMemset(t->dhead_lo, 0, rows * kDheadLd * sizeof(float)));
+        size_t ws = 0;
+        auto upd = [&](size_t b) { if (b > ws) ws = b; };
+        upd(gemm_tc_split_workspace_bytes(2, kHid, kZDim, (int)rows));
+        upd(gemm_tc_split_workspace_bytes(2, kHid, kHid, (int)rows));
+        upd(gemm_tc_split_workspace_bytes(2, kHid, kHead, (int)rows));
+        t->ws_bytes = ws;
+        if (ws) FI_CUDA_OK(cudaMalloc(&t->ws, ws));
+        return FI_OK;
+    }
     p->act.assign(5, nullptr);
     for (int i = 0; i < 5; i++) FI_CUDA_OK(cudaMalloc((void**)&p->act[i], rows * kHid * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&p->d_a, rows * kHid * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&p->d_b, rows * kHid * sizeof(float)));
-    FI_CUDA_OK(cudaMalloc((void**)&p->head, rows * kHead * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&p->dhead, rows * kHead * sizeof(float)));
-    size_t ws = 0;
-    const int mode = l->cfg.gemm_mode;
-    auto upd = [&](size_t b) { if (b > ws) ws = b; };
-    upd(gemm_workspace_bytes(mode, 2, kHid, kZDim, (int)rows));
-    upd(gemm_workspace_bytes(mode, 2, kHid, kHid, (int)rows));
-    upd(gemm_workspace_bytes(mode, 2, kHead, kHid, (int)rows));
-    upd(gemm_workspace_bytes(mode, 0, (int)rows, kHid, kHid));
-    upd(gemm_workspace_bytes(mode, 1, (int)rows, kHid, kHid));
-    p->gemm_ws_bytes = ws;
-    if (ws) FI_CUDA_OK(cudaMalloc(&p->gemm_ws, ws));
-    p->colsum_ws_bytes = colsum_workspace_bytes((int)rows, kHid);
-    FI_CUDA_OK(cudaMalloc(&p->colsum_ws, p->colsum_ws_bytes));
+    p->gemm_ws_bytes = gemm_simt_workspace_bytes(2, kHid, kHid, (int)rows);
+    if (p->gemm_ws_bytes) FI_CUDA_OK(cudaMalloc(&p->gemm_ws, p->gemm_ws_bytes));
     return FI_OK;
 }
 
@@ -36,63 +84,139 @@ void ac_free(Player* p) {
     p->act.clear();
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.clear();
+    if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
+        float* f[] = {t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
+                      t->d_hi[1], t->d_lo[0], t->d_lo[1]};
+        for (float* x : f) if (x) cudaFree(x);
+        for (int i = 0; i < 5; i++) {
+            if (t->act_hi[i]) cudaFree(t->act_hi[i]);
+            if (t->act_lo[i]) cudaFree(t->act_lo[i]);
+        }
+        if (t->ws) cudaFree(t->ws);
+        delete t;
+        p->ac_tc = nullptr;
+    }
 }
 
-static int ac_forward(fi_learner* l, const float* params, const float* in, int ld_in, int rows,
-                      float* const* act, float* head, void* ws, size_t ws_bytes, cudaStream_t st) {
+int ac_activation(Player* p, int layer, const float** a, const float** lo) {
+    if (layer < 0 || layer >= 5) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
+    if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
+        *a = t->act_hi[layer];
+        *lo = t->act_lo[layer];
+    } else {
+        *a = p->act[layer];
+        *lo = nullptr;
+    }
+    return FI_OK;
+}
+
+// ---------------------------------------------------------------- SIMT path ------------------
+static int ac_forward_simt(fi_learner* l, const float* params, const float* in, int ld_in, int rows,
+                           float* const* act, float* head, void* ws, size_t ws_bytes, cudaStream_t st) {
     const auto& T = l->tensors;
-    const int mode = l->cfg.gemm_mode;
     const float* x = in;
     int ldx = ld_in, k = kZDim;
     for (int layer = 0; layer < 5; layer++) {
-        FI_TRY(launch_gemm(mode, 0, rows, kHid, k, x, ldx, params + T[2 * layer].offset, k, act[layer], kHid,
-                           params + T[2 * layer + 1].offset, 1, nullptr, 0, ws, ws_bytes, st));
+        FI_TRY(launch_gemm_simt(0, rows, kHid, k, x, ldx, params + T[2 * layer].offset, k, act[layer], kHid,
+                                params + T[2 * layer + 1].offset, 1, nullptr, 0, ws, ws_bytes, st));
         x = act[layer];
         ldx = kHid;
         k = kHid;
     }
-    return launch_gemm(mode, 0, rows, kHead, kHid, x, kHid, params + T[10].offset, kHid, head, kHead,
-                       params + T[11].offset, 0, nullptr, 0, ws, ws_bytes, st);
+    return launch_gemm_simt(0, rows, kHead, kHid, x, kHid, params + T[10].offset, kHid, head, kHead,
+                            params + T[11].offset, 0, nullptr, 0, ws, ws_bytes, st);
 }
 
-int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int /*global_m*/) {
+static int ac_forward_backward_simt(fi_learner* l, Player* p, const float* batch, int m, int t) {
     const auto& T = l->tensors;
     const auto& c = l->cfg;
-    const int rows = m * t, mode = c.gemm_mode;
+    const int rows = m * t;
     cudaStream_t st = p->stream;
-    FI_TRY(ac_forward(l, p->params, batch, kRecWords, rows, p->act.data(), p->head, p->gemm_ws, p->gemm_ws_bytes, st));
+    FI_TRY(ac_forward_simt(l, p->params, batch, kRecWords, rows, p->act.data(), p->head, p->gemm_ws, p->gemm_ws_bytes, st));
     FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
     FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                    c.baseline_cost, c.entropy_cost, p->dhead, nullptr, nullptr, p->d_losses, st));
     // head: dW = dhead^T act4, db = colsum(dhead), d4 = (dhead Wh) * relu'(act4)
     float* g = p->grads;
     FI_TRY(launch_colsum(p->dhead, kHead, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
-    FI_TRY(launch_gemm(mode, 2, kHead, kHid, rows, p->dhead, kHead, p->act[4], kHid, g + T[10].offset, kHid, nullptr,
-                       0, nullptr, 0, p->gemm_ws, p->gemm_ws_bytes, st));
+    FI_TRY(launch_gemm_simt(2, kHead, kHid, rows, p->dhead, kHead, p->act[4], kHid, g + T[10].offset, kHid, nullptr,
+                            0, nullptr, 0, p->gemm_ws, p->gemm_ws_bytes, st));
     float* d = p->d_a;
     float* d_next = p->d_b;
-    FI_TRY(launch_gemm(mode, 1, rows, kHid, kHead, p->dhead, kHead, p->params + T[10].offset, kHid, d, kHid, nullptr,
-                       0, p->act[4], kHid, p->gemm_ws, p->gemm_ws_bytes, st));
+    FI_TRY(launch_gemm_simt(1, rows, kHid, kHead, p->dhead, kHead, p->params + T[10].offset, kHid, d, kHid, nullptr,
+                            0, p->act[4], kHid, p->gemm_ws, p->gemm_ws_bytes, st));
     for (int layer = 4; layer >= 0; layer--) {
         const float* in = layer == 0 ? batch : p->act[layer - 1];
         const int ld_in = layer == 0 ? kRecWords : kHid, k = layer == 0 ? kZDim : kHid;
         FI_TRY(launch_colsum(d, kHid, rows, kHid, g + T[2 * layer + 1].offset, p->colsum_ws, p->colsum_ws_bytes, st));
-        FI_TRY(launch_gemm(mode, 2, kHid, k, rows, d, kHid, in, ld_in, g + T[2 * layer].offset, k, nullptr, 0, nullptr,
-                           0, p->gemm_ws, p->gemm_ws_bytes, st));
+        FI_TRY(launch_gemm_simt(2, kHid, k, rows, d, kHid, in, ld_in, g + T[2 * layer].offset, k, nullptr, 0, nullptr,
+                                0, p->gemm_ws, p->gemm_ws_bytes, st));
         if (layer > 0) {
-            FI_TRY(launch_gemm(mode, 1, rows, kHid, kHid, d, kHid, p->params + T[2 * layer].offset, kHid, d_next, kHid,
-                               nullptr, 0, p->act[layer - 1], kHid, p->gemm_ws, p->gemm_ws_bytes, st));
+            FI_TRY(launch_gemm_simt(1, rows, kHid, kHid, d, kHid, p->params + T[2 * layer].offset, kHid, d_next, kHid,
+                                    nullptr, 0, p->act[layer - 1], kHid, p->gemm_ws, p->gemm_ws_bytes, st));
             float* tmp = d; d = d_next; d_next = tmp;
         }
     }
     return FI_OK;
 }
 
-int ac_activation(Player* p, int layer, const float** a, const float** lo) {
-    if (layer < 0 || layer >= (int)p->act.size()) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
-    *a = p->act[layer];
-    *lo = nullptr;
+// ---------------------------------------------------------------- tensor-core path -----------
+static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, int m, int t) {
+    const auto& T = l->tensors;
+    const auto& c = l->cfg;
+    AcTc* tc = static_cast<AcTc*>(p->ac_tc);
+    const int rows = m * t;
+    cudaStream_t st = p->stream;
+    float* g = p->grads;
+    // pre-passes: weights (4.6 MB) and observations -> hi/lo pairs
+    FI_TRY(launch_split_tf32(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, (int)l->arena_elems, tc->w_hi, tc->w_lo, st));
+    FI_TRY(launch_split_tf32(p->params + T[0].offset, kZDim, kHid, kZDim, kObsLd, tc->w1_hi, tc->w1_lo, st));
+    FI_TRY(launch_split_tf32(batch, kRecWords, (size_t)rows, kZDim, kObsLd, tc->obs_hi, tc->obs_lo, st));
+    auto W = [&](int tensor, int ld) { return SplitMat{tc->w_hi + T[tensor].offset, tc->w_lo + T[tensor].offset, ld}; };
+    auto ACT = [&](int layer) { return SplitMat{tc->act_hi[layer], tc->act_lo[layer], kHid}; };
+    const SplitMat obs{tc->obs_hi, tc->obs_lo, kObsLd}, w1{tc->w1_hi, tc->w1_lo, kObsLd};
+    // forward: x_l = relu(x_{l-1} W_l^T + b_l), written as hi/lo pairs by the GEMM epilogue
+    for (int layer = 0; layer < 5; layer++) {
+        const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
+        const SplitMat w = layer == 0 ? w1 : W(2 * layer, kHid);
+        const TcOut out{nullptr, 0, tc->act_hi[layer], tc->act_lo[layer], kHid, 0};
+        FI_TRY(launch_gemm_tc_split(0, rows, kHid, layer == 0 ? kZDim : kHid, x, w, out, p->params + T[2 * layer + 1].offset, 1,
+                                    nullptr, 0, nullptr, 0, st));
+    }
+    FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0},
+                                p->params + T[11].offset, 0, nullptr, 0, nullptr, 0, st));
+    FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
+    FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
+                                   c.baseline_cost, c.entropy_cost, nullptr, nullptr, nullptr, p->d_losses, st, tc->dhead_hi,
+                                   tc->dhead_lo, kDheadLd));
+    const SplitMat dhead{tc->dhead_hi, tc->dhead_lo, kDheadLd};
+    // head: db = colsum(dhead); dWh^T [512,17] = act4^T dhead, stored transposed as dWh [17,512];
+    // d4 = (dhead Wh) * relu'(act4)
+    FI_TRY(launch_colsum2(tc->dhead_hi, tc->dhead_lo, kDheadLd, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
+    FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, TcOut{g + T[10].offset, kHid, nullptr, nullptr, 0, 1}, nullptr,
+                                0, nullptr, 0, tc->ws, tc->ws_bytes, st));
+    int cur = 0;
+    FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHead, dhead, W(10, kHid), TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0},
+                                nullptr, 0, tc->act_hi[4], kHid, nullptr, 0, st));
+    for (int layer = 4; layer >= 0; layer--) {
+        const SplitMat d{tc->d_hi[cur], tc->d_lo[cur], kHid};
+        const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
+        const int k = layer == 0 ? kZDim : kHid;
+        FI_TRY(launch_colsum2(d.hi, d.lo, kHid, rows, kHid, g + T[2 * layer + 1].offset, p->colsum_ws, p->colsum_ws_bytes, st));
+        FI_TRY(launch_gemm_tc_split(2, kHid, k, rows, d, x, TcOut{g + T[2 * layer].offset, k, nullptr, nullptr, 0, 0}, nullptr, 0,
+                                    nullptr, 0, tc->ws, tc->ws_bytes, st));
+        if (layer > 0) {
+            FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHid, d, W(2 * layer, kHid),
+                                        TcOut{nullptr, 0, tc->d_hi[cur ^ 1], tc->d_lo[cur ^ 1], kHid, 0}, nullptr, 0,
+                                        tc->act_hi[layer - 1], kHid, nullptr, 0, st));
+            cur ^= 1;
+        }
+    }
     return FI_OK;
+}
+
+int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int /*global_m*/) {
+    return p->ac_tc ? ac_forward_backward_tc(l, p, batch, m, t) : ac_forward_backward_simt(l, p, batch, m, t);
 }
 
 int ac_infer_alloc(fi_learner* /*l*/, Player* p, size_t rows) {
@@ -102,11 +226,12 @@ int ac_infer_alloc(fi_learner* /*l*/, Player* p, size_t rows) {
     return FI_OK;
 }
 
-// Batched actor policy inference: the same forward GEMM kernels on the
+// Batched actor policy inference: the forward GEMM kernels on the
 // published device snapshot of the weights. obs_dev [rows,162] -> out_dev [rows,17].
+// Actor batches are small (tens to hundreds of rows), so this uses the fp32 FFMA kernels.
 int ac_infer(fi_learner* l, Player* p, const float* params, const float* obs_dev, size_t rows, float* out_dev,
              cudaStream_t stream) {
-    return ac_forward(l, params, obs_dev, kZDim, (int)rows, p->inf_act.data(), out_dev, nullptr, 0, stream);
+    return ac_forward_simt(l, params, obs_dev, kZDim, (int)rows, p->inf_act.data(), out_dev, nullptr, 0, stream);
 }
 
 }  // namespace fi

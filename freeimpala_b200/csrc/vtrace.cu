@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(128)
 vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const float* __restrict__ head, int ldh,
                         float rho_bar, float c_bar, float pg_rho_bar, float lambda_, float baseline_cost,
                         float entropy_cost, float* __restrict__ dhead, float* __restrict__ vs_out,
-                        float* __restrict__ adv_out, double* __restrict__ losses) {
+                        float* __restrict__ adv_out, double* __restrict__ losses, float* __restrict__ dhead_hi,
+                        float* __restrict__ dhead_lo, int ld_split) {
     const int lane = threadIdx.x & 31;
     const int traj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (traj >= m) return;
@@ -226,14 +227,29 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
         if (lane == 31 || s >= t - 1) vs_next = vs_next_chunk;
         const float adv = fminf(pg_rho_bar, is) * (r + g * vs_next - v);
         if (valid) {
-            float* dh = dhead + row * ldh;
+            float dv[kHead];
 #pragma unroll
             for (int j = 0; j < kNumActions; j++) {
                 const float d_pg = adv * (p[j] - (j == act ? 1.f : 0.f));
                 const float d_ent = p[j] * (z[j] - plogp);
-                dh[j] = fmaf(entropy_cost, d_ent, d_pg);
+                dv[j] = fmaf(entropy_cost, d_ent, d_pg);
             }
-            dh[kNumActions] = -baseline_cost * (vs - v);
+            dv[kNumActions] = -baseline_cost * (vs - v);
+            if (dhead) {
+                float* dh = dhead + row * ldh;
+#pragma unroll
+                for (int j = 0; j < kHead; j++) dh[j] = dv[j];
+            }
+            if (dhead_hi) {  // hi/lo pair for the tcgen05 3xTF32 GEMMs of the backward pass
+                float* dhh = dhead_hi + row * ld_split;
+                float* dhl = dhead_lo + row * ld_split;
+#pragma unroll
+                for (int j = 0; j < kHead; j++) {
+                    const float h = __uint_as_float(__float_as_uint(dv[j]) & 0xFFFFE000u);
+                    dhh[j] = h;
+                    dhl[j] = dv[j] - h;
+                }
+            }
             if (vs_out) vs_out[row] = vs;
             if (adv_out) adv_out[row] = adv;
             l_pg += (double)(-logp_a * adv);
@@ -258,9 +274,10 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
 int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar,
                             float c_bar, float pg_rho_bar, float lambda_, float baseline_cost,
                             float entropy_cost, float* dhead, float* vs, float* pg_adv, double* losses,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, float* dhead_hi, float* dhead_lo, int ld_split) {
     if (m <= 0 || t <= 0) return FI_OK;
-    if (!batch || !head || !dhead || !losses || ldh < kHead) return set_error(FI_ERR_ARG, "vtrace loss head: bad argument");
+    if (!batch || !head || (!dhead && !dhead_hi) || !losses || ldh < kHead || (dhead_hi && (!dhead_lo || ld_split < kHead)))
+        return set_error(FI_ERR_ARG, "vtrace loss head: bad argument");
     const int warps = 4;
     // algorithmic traffic per transition: head row in (17 x 4 B) + dhead row out (17 x 4 B) + the record's
     // behaviour logits, action, reward, discount (19 x 4 B) = 212 B (+ 8 B when vs / pg_adv are written)
@@ -268,7 +285,7 @@ int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, 
                    (212.0 + (vs ? 4.0 : 0.0) + (pg_adv ? 4.0 : 0.0)) * (double)m * t, kWorkBytes);
     vtrace_loss_head_kernel<<<(m + warps - 1) / warps, 32 * warps, 0, stream>>>(
         (const float*)batch, m, t, head, ldh, rho_bar, c_bar, pg_rho_bar, lambda_, baseline_cost, entropy_cost,
-        dhead, vs, pg_adv, losses);
+        dhead, vs, pg_adv, losses, dhead_hi, dhead_lo, ld_split);
     return ls.done();
 }
 
