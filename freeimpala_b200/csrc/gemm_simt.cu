@@ -6,7 +6,7 @@
 //   dgrad    dX[m,k] = dY[m,n] W[n,k]  (* relu'(X))      A k-contiguous, B n-contiguous
 //   wgrad    dW[n,k] = dY[m,n]^T X[m,k]                  A m-contiguous, B m-contiguous, split-K
 // CTA tile 128 x BN x 16, 256 threads, 8 x (BN/16) register tile, double-buffered shared memory.
-#include "fi_common.cuh"
+#include "fi_internal.cuh"
 
 namespace fi {
 

@@ -9,7 +9,7 @@
 // The reverse-time first-order recurrence is associative under (a1,b1)o(a2,b2) =
 // (a1 a2, b1 + a1 b2), so each warp scans 32 time steps at once with shuffles and carries one
 // scalar across 32-step chunks (last chunk first).
-#include "fi_common.cuh"
+#include "fi_internal.cuh"
 
 namespace fi {
 
