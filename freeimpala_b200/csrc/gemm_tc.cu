@@ -50,8 +50,12 @@ struct TcEpilogue {
     const float* bias;   // [n] or null
     const float* mask;   // [m, ldmask]: out = mask > 0 ? out : 0 (ReLU backward), or null
     int ldmask;
+    const uint32_t* mask_bits;  // bit-packed ReLU decisions [m, mask_ldw words] (bit j of word w = column 32w + j), or null
+    uint32_t* mask_bits_out;    // written by a ReLU epilogue for the backward pass, or null
+    int mask_ldw;
     int relu;
     int transpose_out;   // c[col * ldc + row] (plain output only)
+    int tma_split;       // c_hi / c_lo are written with TMA stores (map_c_hi / map_c_lo are valid)
     size_t split_stride; // elements between split-K slabs of c
 };
 
@@ -90,6 +94,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,7 +155,8 @@ struct TcCfg {
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static constexpr int kStages = BN >= 128 ? 3 : 4;
     static constexpr int kTmemCols = 4 * BN;                          // main[2] + corr[2] (a power of two >= 32)
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kOutTileBytes = 4 * 2 * 32 * 128;            // per epilogue warp: hi + lo staging tiles of 32 x 128 B
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
 };
 
@@ -150,6 +165,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
                const TcShape sh, const TcEpilogue ep) {
     using Cfg = TcCfg<BN>;
     constexpr int kStages = Cfg::kStages;
@@ -159,7 +175,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
     // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2], corr_empty[2]
-    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    const uint32_t out_tiles = smem_base + kStages * Cfg::kStageBytes;    // 1024-byte aligned: TMA-store staging, 8 KB per warp
+    const uint32_t bar_base = out_tiles + Cfg::kOutTileBytes;
     const uint32_t tmem_slot = bar_base + (2 * kStages + 6) * 8;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -297,6 +314,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float acc[BN];
 #pragma unroll
             for (int i = 0; i < BN; i++) acc[i] = 0.f;
+            // bit-packed ReLU mask of this thread's row: one 16-byte load per tile, issued before the k-loop so that
+            // its latency hides behind the MMAs (a float mask read in the epilogue was latency-bound: 4 warps per SM)
+            uint32_t mw[BN / 32];
+#pragma unroll
+            for (int c = 0; c < BN / 32; c++) mw[c] = 0xFFFFFFFFu;
+            if (ep.mask_bits && row_ok) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++)
+                    if (n0 + c * 32 < sh.n) mw[c] = __ldg(ep.mask_bits + (size_t)row * ep.mask_ldw + (n0 >> 5) + c);
+            }
             for (int kc = kb0; kc < kb1; kc += kTcChunk) {
                 mbar_wait(main_full_bar(mb), mphase);
                 tc_fence_after();
@@ -326,71 +353,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(corr_empty_bar(cb));
             cb ^= 1;
-            if (!row_ok) continue;
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
+            if (ep.transpose_out) {
+                // c[col * ldc + row]: lanes hold consecutive rows, so the register layout is already coalesced
+                if (row_ok && cplain) {
 #pragma unroll
-            for (int c = 0; c < BN / 32; c++) {
-                const int col0 = n0 + c * 32;
-                if (col0 < sh.n) {
-                    float x[32];
+                    for (int c = 0; c < BN / 32; c++) {
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        float t = acc[c * 32 + i];
-                        const int col = col0 + i;
-                        if (col < sh.n) {
-                            if (ep.bias) t += __ldg(ep.bias + col);
-                            if (ep.relu) t = fmaxf(t, 0.f);
-                            if (ep.mask) t = __ldg(ep.mask + (size_t)row * ep.ldmask + col) > 0.f ? t : 0.f;
-                        }
-                        x[i] = t;
-                    }
-                    const bool full = col0 + 32 <= sh.n;
-                    if (cplain) {
-                        if (ep.transpose_out) {
-#pragma unroll
-                            for (int i = 0; i < 32; i++)
-                                if (col0 + i < sh.n) cplain[(size_t)(col0 + i) * ep.ldc + row] = x[i];
-                        } else {
-                            float* dst = cplain + (size_t)row * ep.ldc + col0;
-                            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; i++)
-                                    if (col0 + i < sh.n) dst[i] = x[i];
-                            }
-                        }
-                    }
-                    if (ep.c_hi) {
-                        float* dh = ep.c_hi + (size_t)row * ep.ldc_split + col0;
-                        float* dl = ep.c_lo + (size_t)row * ep.ldc_split + col0;
-                        if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0)) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 h, l;
-                                h.x = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u); l.x = x[i] - h.x;
-                                h.y = __uint_as_float(__float_as_uint(x[i + 1]) & 0xFFFFE000u); l.y = x[i + 1] - h.y;
-                                h.z = __uint_as_float(__float_as_uint(x[i + 2]) & 0xFFFFE000u); l.z = x[i + 2] - h.z;
-                                h.w = __uint_as_float(__float_as_uint(x[i + 3]) & 0xFFFFE000u); l.w = x[i + 3] - h.w;
-                                *reinterpret_cast<float4*>(dh + i) = h;
-                                *reinterpret_cast<float4*>(dl + i) = l;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i++)
-                                if (col0 + i < sh.n) {
-                                    const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
-                                    dh[i] = h;
-                                    dl[i] = x[i] - h;
-                                }
+                        for (int i = 0; i < 32; i++) {
+                            const int col = n0 + c * 32 + i;
+                            if (col < sh.n) cplain[(size_t)col * ep.ldc + row] = acc[c * 32 + i];
                         }
                     }
                 }
+                continue;
+            }
+            if (ep.mask_bits) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[c * 32 + i] = ((mw[c] >> i) & 1u) ? acc[c * 32 + i] : 0.f;
+                }
+            }
+            if (ep.tma_split) {
+                // hi/lo pair output: bias, ReLU, the split and the ReLU bit mask are computed in registers (lane = row),
+                // the 32 x 32 block goes to this warp's 128B-swizzled staging tiles with conflict-free 16-byte stores, and
+                // one lane hands both tiles to the TMA (cp.async.bulk.tensor store): no per-element address arithmetic
+                // and no store instructions on the critical path of the 4 promotion warps. Rows / columns beyond the
+                // matrix are clipped by the TMA.
+                const uint32_t out_hi = out_tiles + (uint32_t)q * 8192u, out_lo = out_hi + 4096u;
+                const int rbase = m0 + q * 32;
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= sh.n) continue;  // warp-uniform
+                    if (lane == 0) tma_store_wait_read();  // the previous block's stores have left the staging tiles
+                    __syncwarp();
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float t[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int i = 4 * j + e;
+                            float x = acc[c * 32 + i];
+                            if (ep.bias && col0 + i < sh.n) x += __ldg(ep.bias + col0 + i);
+                            if (ep.relu) x = fmaxf(x, 0.f);
+                            bits |= (x > 0.f ? 1u : 0u) << i;
+                            t[e] = x;
+                        }
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(t[0]) & 0xFFFFE000u); l.x = t[0] - h.x;
+                        h.y = __uint_as_float(__float_as_uint(t[1]) & 0xFFFFE000u); l.y = t[1] - h.y;
+                        h.z = __uint_as_float(__float_as_uint(t[2]) & 0xFFFFE000u); l.z = t[2] - h.z;
+                        h.w = __uint_as_float(__float_as_uint(t[3]) & 0xFFFFE000u); l.w = t[3] - h.w;
+                        const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);  // 128B swizzle
+                        st_shared_v4(out_hi + off, h);
+                        st_shared_v4(out_lo + off, l);
+                    }
+                    if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_c_hi, out_hi, col0, rbase);
+                        tma_store_2d(&map_c_lo, out_lo, col0, rbase);
+                        tma_store_commit();
+                    }
+                }
+                continue;
+            }
+            // Row-major outputs: each lane holds 32 consecutive columns of ITS row, which would make every store
+            // instruction touch 32 different rows. Transpose each 32x32 block through this warp's padded shared-memory
+            // tile so that a store instruction writes 128 contiguous bytes of one row; bias, ReLU and the hi/lo split are
+            // applied after the transpose, where lane = column.
+            float* stg = reinterpret_cast<float*>(smem_raw + (out_tiles - smem_u32(smem_raw)) + q * 8192);  // [32][33] floats
+            const int rbase = m0 + q * 32;
+            const int rows_here = min(32, sh.m - rbase);
+#pragma unroll
+            for (int c = 0; c < BN / 32; c++) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= sh.n || rows_here <= 0) continue;  // warp-uniform
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; i++) stg[lane * 33 + i] = acc[c * 32 + i];
+                __syncwarp();
+                const int col = col0 + lane;
+                const bool col_ok = col < sh.n;
+                const float bias = (ep.bias && col_ok) ? __ldg(ep.bias + col) : 0.f;
+                float* pc = cplain ? cplain + (size_t)rbase * ep.ldc + col : nullptr;
+                float* ph = ep.c_hi ? ep.c_hi + (size_t)rbase * ep.ldc_split + col : nullptr;
+                float* pl = ep.c_hi ? ep.c_lo + (size_t)rbase * ep.ldc_split + col : nullptr;
+                const float* pm = ep.mask ? ep.mask + (size_t)rbase * ep.ldmask + col : nullptr;
+                uint32_t myword = 0;
+#pragma unroll 1
+                for (int rr0 = 0; rr0 < 32; rr0 += 8) {  // 8 rows per batch: 8 shared-memory reads in flight per lane
+                    float tv[8], mv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        tv[u] = stg[(rr0 + u) * 33 + lane];
+                        mv[u] = 1.f;
+                        if (pm && col_ok && rr0 + u < rows_here) mv[u] = __ldg(pm + (size_t)u * ep.ldmask);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        float t = tv[u] + bias;
+                        if (ep.relu) t = fmaxf(t, 0.f);
+                        t = mv[u] > 0.f ? t : 0.f;
+                        if (ep.mask_bits_out) {
+                            const uint32_t w32 = __ballot_sync(0xFFFFFFFFu, col_ok && t > 0.f);
+                            if (lane == rr0 + u) myword = w32;
+                        }
+                        if (col_ok && rr0 + u < rows_here) {
+                            if (pc) pc[(size_t)u * ep.ldc] = t;
+                            if (ph) {
+                                const float h = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);
+                                ph[(size_t)u * ep.ldc_split] = h;
+                                pl[(size_t)u * ep.ldc_split] = t - h;
+                            }
+                        }
+                    }
+                    if (pc) pc += (size_t)8 * ep.ldc;
+                    if (ph) { ph += (size_t)8 * ep.ldc_split; pl += (size_t)8 * ep.ldc_split; }
+                    if (pm) pm += (size_t)8 * ep.ldmask;
+                }
+                if (ep.mask_bits_out && lane < rows_here)
+                    ep.mask_bits_out[(size_t)(rbase + lane) * ep.mask_ldw + (col0 >> 5)] = myword;
             }
         }
     }
 
+    if (warp >= 4 && lane == 0) tma_store_wait_all();  // staged output tiles must outlive their bulk stores
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -489,8 +581,10 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
         FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    LaunchScope ls("gemm_tc_kernel", st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], sh, ep);
+    // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
+    const char* label = !B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>");
+    LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
+    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
     return ls.done();
 }
 
@@ -512,9 +606,12 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     TcEpilogue ep;
     ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
+    ep.mask_bits = out.mask_bits_in; ep.mask_bits_out = out.mask_bits_out; ep.mask_ldw = out.mask_ldw;
+    if (ep.mask_bits && (bias || relu || (n > 32 && (ep.mask_ldw % 4 || (reinterpret_cast<uintptr_t>(ep.mask_bits) & 15)))))
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM: a bit mask excludes bias/ReLU and needs 16-byte aligned rows");
     if (sh.num_splits > 1) {
         const size_t need = (size_t)sh.num_splits * m * n * sizeof(float);
-        if (!workspace || workspace_bytes < need || bias || relu || mask || out.c_hi || !out.c) {
+        if (!workspace || workspace_bytes < need || bias || relu || mask || out.c_hi || !out.c || out.mask_bits_in || out.mask_bits_out) {
             sh.num_splits = 1;  // no room for partials (or an epilogue is requested): one split per tile
         } else {
             ep.c = static_cast<float*>(workspace);
@@ -525,7 +622,7 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     }
     sh.kb_per_split = (sh.num_kb + sh.num_splits - 1) / sh.num_splits;
     sh.num_splits = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;
-    CUtensorMap maps[4];
+    CUtensorMap maps[6];
     if (!a_mn) {
         FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
         FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
@@ -539,6 +636,16 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     } else {
         FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
         FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
+    }
+    ep.tma_split = 0;
+    if (ep.c_hi && !ep.transpose_out && out.ld_split % 4 == 0 && ((reinterpret_cast<uintptr_t>(ep.c_hi) | reinterpret_cast<uintptr_t>(ep.c_lo)) & 15) == 0 &&
+        !ep.c && !ep.mask) {
+        FI_TRY(make_map(&maps[4], ep.c_hi, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false));
+        FI_TRY(make_map(&maps[5], ep.c_lo, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false));
+        ep.tma_split = 1;
+    } else {
+        maps[4] = maps[0];
+        maps[5] = maps[0];
     }
     const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
@@ -594,7 +701,7 @@ int launch_gemm_tc(int trans, int m, int n, int k, const float* a, int lda, cons
     FI_TRY(launch_split_tf32(a, lda, a_rows, (int)a_cols, (int)a_ld, a_hi, a_lo, st));
     FI_TRY(launch_split_tf32(b, ldb, b_rows, (int)b_cols, (int)b_ld, b_hi, b_lo, st));
     SplitMat sa{a_hi, a_lo, (int)a_ld}, sb{b_hi, b_lo, (int)b_ld};
-    TcOut out{c, ldc, nullptr, nullptr, 0, 0};
+    TcOut out{c, ldc, nullptr, nullptr, 0, 0, nullptr, nullptr, 0};
     const size_t split_ws = gemm_tc_split_workspace_bytes(trans, m, n, k);
     if (trans == 2 && ldc != n) {  // split-K partials need a dense output
         return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, nullptr, 0, st);

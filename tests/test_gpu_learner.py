@@ -48,7 +48,8 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
         want, n_over, max_over = O.loss_grad_masked(obs, mu, act, rew, disc, boot, masks)
         assert n_over <= 4 + 2e-5 * masks.size and max_over < 1e-5, (n_over, max_over)
         np.testing.assert_allclose(got, want, rtol=TOL, atol=1e-6 * abs(want[0]))
-        np.testing.assert_allclose(got, want_free, rtol=TOL, atol=1e-6 * abs(want[0]))
+        # the free-running oracle drifts after the first update (see AdamParity): sanity bound only
+        np.testing.assert_allclose(got, want_free, rtol=TOL if s == 0 else 1e-3, atol=1e-6 * abs(want[0]))
         grads = L.get_grads(0)
         assert U.rel_l2(grads, O.grads()) < TOL
         L.apply_update(0)
