@@ -53,6 +53,7 @@ SIGNATURES = {
     "fi_ring_destroy": (None, [_P]),
     "fi_ring_write": (c_int, [_P, _P, c_size_t]),
     "fi_ring_try_write": (c_int, [_P, _P, c_size_t]),
+    "fi_ring_write_many": (c_size_t, [_P, _P, c_size_t, c_size_t, c_size_t]),
     "fi_ring_reserve": (_P, [_P, C.POINTER(c_u64)]),
     "fi_ring_commit": (c_int, [_P, c_u64, c_size_t]),
     "fi_ring_read_batch": (c_int, [_P, c_size_t, _P, C.POINTER(FiBatch)]),

@@ -8,8 +8,8 @@
 //     main += A_hi B_hi            corr += A_hi B_lo + A_lo B_hi      (A_lo B_lo ~ 2^-22 relative is dropped).
 // Measured on B200: the tensor core adds into its fp32 accumulator with truncation, ~1 ulp of the
 // running sum per MMA, biased towards zero (error grew linearly with K: 2.4e-5 at K=32, 4.6e-4 at K=512
-// on sums of magnitude ~20). The big products therefore accumulate in TMEM only over a CHUNK of 4
-// k-blocks (16 MMAs); the promotion warps then add the chunk to fp32 register accumulators with
+// on sums of magnitude ~20). The big products therefore accumulate in TMEM only over a CHUNK of 2
+// k-blocks (8 MMAs); the promotion warps then add the chunk to fp32 register accumulators with
 // round-to-nearest (the scheme of Ootomo & Yokota 2022, at chunk granularity). The correction
 // terms are 2^-11 smaller, so their own truncation is harmless and they stay in TMEM per tile.
 //
@@ -38,7 +38,7 @@ namespace fi {
 constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int kTcThreads = 256;
-constexpr int kTcChunk = 4;      // k-blocks accumulated in TMEM before promotion to registers (16 main MMAs)
+constexpr int kTcChunk = 2;      // k-blocks accumulated in TMEM before promotion to registers (8 main MMAs)
 constexpr int kTcSmemLimit = 227 * 1024;
 
 struct TcEpilogue {

@@ -223,6 +223,13 @@ static int ring_write_impl(fi_ring* r, const void* src, size_t n, bool blocking)
 int fi_ring_write(fi_ring* ring, const void* src, size_t n) { return ring_write_impl(ring, src, n, true); }
 int fi_ring_try_write(fi_ring* ring, const void* src, size_t n) { return ring_write_impl(ring, src, n, false); }
 
+size_t fi_ring_write_many(fi_ring* ring, const void* src, size_t count, size_t stride, size_t n) {
+    size_t done = 0;
+    for (; done < count; done++)
+        if (!ring_write_impl(ring, static_cast<const unsigned char*>(src) + done * stride, n, true)) break;
+    return done;
+}
+
 void* fi_ring_reserve(fi_ring* r, uint64_t* ticket) {
     if (!r) return nullptr;
     size_t slot;

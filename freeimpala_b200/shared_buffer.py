@@ -96,6 +96,12 @@ class SharedBuffer:
         keep, ptr, n = _as_bytes_view(data)
         return bool(self._lib.fi_ring_try_write(self._h, ptr, n))
 
+    def write_many(self, array: np.ndarray) -> int:
+        """Write every row of a C-contiguous 2-D uint8 array as one entry (one boundary crossing)."""
+        a = np.ascontiguousarray(array)
+        assert a.ndim == 2
+        return self._lib.fi_ring_write_many(self._h, a.ctypes.data, a.shape[0], a.strides[0], a.shape[1] * a.itemsize)
+
     def reserve(self):
         """Zero-copy producer: (numpy view of the pinned slot, ticket)."""
         ticket = C.c_uint64()

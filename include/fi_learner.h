@@ -92,6 +92,11 @@ FI_API int fi_ring_write(fi_ring* ring, const void* src, size_t n);
  * is full, or n > slot_bytes; never blocks on ring state. */
 FI_API int fi_ring_try_write(fi_ring* ring, const void* src, size_t n);
 
+/* `count` consecutive fi_ring_write calls in one crossing of the boundary (an MPI receiver or a foreign-
+ * language actor handing over a burst of trajectories): entry i is the n bytes at src + i * stride. Returns
+ * the number of entries written (stops at the first one that fi_ring_write would reject). */
+FI_API size_t fi_ring_write_many(fi_ring* ring, const void* src, size_t count, size_t stride, size_t n);
+
 /* Zero-copy producer: reserve the next pinned slot (blocks
  * while full), let the caller fill it in place (e.g. MPI_Irecv straight into it), then
  * commit n bytes. Slots commit in reservation order. */
