@@ -28,98 +28,131 @@ __device__ __forceinline__ void warp_reverse_linear_scan(float& a, float& b, int
 }
 
 // ---------------------------------------------------------------- standalone scan -------
-// Arrays are trajectory-major [m, t] fp32. One CTA stages `tr` consecutive trajectories
-// (a contiguous span of tr*t floats per array) into shared memory with 16-byte coalesced
-// loads, each warp scans one trajectory out of shared memory, and the two result spans are
-// written back with 16-byte coalesced stores. Algorithmic traffic: 16 B in + 8 B out per
-// transition (+4 B per trajectory for the bootstrap); HBM-bound.
-__device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* __restrict__ src, size_t e0,
-                                         int count, bool vec_ok) {
-    if (vec_ok) {
-        const float4* s4 = reinterpret_cast<const float4*>(src + e0);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        const int n4 = count >> 2;
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(s4 + i);
-        for (int i = (n4 << 2) + threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + e0 + i);
-    } else {
-        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + e0 + i);
+// Arrays are trajectory-major [m, t] fp32, so 32 lanes x V consecutive time steps are one coalesced
+// request per array. One warp owns one trajectory and walks it from the end in chunks of 32*V steps:
+// each lane folds its V steps into one (a, b) pair, the warp combines the 32 pairs with shuffles, and
+// the lane unfolds its V results; the next chunk's four loads are issued before the current chunk is
+// computed (register double-buffering). Algorithmic traffic: 16 B in + 8 B out per transition
+// (+4 B per trajectory for the bootstrap); HBM-bound.
+// (Round-1 measurement: the first version staged whole trajectories through shared memory per CTA,
+// load -> __syncthreads -> scan -> __syncthreads -> store, and was latency-bound at 29 % of the HBM
+// roofline on 39 MB; see profiles/.)
+template <int V>
+struct ScanChunk {
+    float lr[V], g[V], r[V], v[V];
+};
+
+template <int V>
+__device__ __forceinline__ void scan_load(ScanChunk<V>& d, const float* __restrict__ log_rho,
+                                          const float* __restrict__ discount, const float* __restrict__ reward,
+                                          const float* __restrict__ value, size_t base, int s0, int t) {
+    if constexpr (V == 4) {
+        if (s0 + 3 < t) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(log_rho + base + s0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(discount + base + s0));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(reward + base + s0));
+            const float4 e = __ldg(reinterpret_cast<const float4*>(value + base + s0));
+            d.lr[0] = a.x; d.lr[1] = a.y; d.lr[2] = a.z; d.lr[3] = a.w;
+            d.g[0] = b.x; d.g[1] = b.y; d.g[2] = b.z; d.g[3] = b.w;
+            d.r[0] = c.x; d.r[1] = c.y; d.r[2] = c.z; d.r[3] = c.w;
+            d.v[0] = e.x; d.v[1] = e.y; d.v[2] = e.z; d.v[3] = e.w;
+            return;
+        }
     }
-}
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* __restrict__ src, size_t e0,
-                                          int count, bool vec_ok) {
-    if (vec_ok) {
-        float4* d4 = reinterpret_cast<float4*>(dst + e0);
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        const int n4 = count >> 2;
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
-        for (int i = (n4 << 2) + threadIdx.x; i < count; i += blockDim.x) dst[e0 + i] = src[i];
-    } else {
-        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[e0 + i] = src[i];
+#pragma unroll
+    for (int e = 0; e < V; e++) {
+        const bool ok = s0 + e < t;
+        d.lr[e] = ok ? __ldg(log_rho + base + s0 + e) : 0.f;
+        d.g[e] = ok ? __ldg(discount + base + s0 + e) : 0.f;
+        d.r[e] = ok ? __ldg(reward + base + s0 + e) : 0.f;
+        d.v[e] = ok ? __ldg(value + base + s0 + e) : 0.f;
     }
 }
 
-__global__ void vtrace_scan_kernel(int m, int t, int tr, const float* __restrict__ log_rho,
-                                   const float* __restrict__ discount, const float* __restrict__ reward,
-                                   const float* __restrict__ value, const float* __restrict__ bootstrap,
-                                   float rho_bar, float c_bar, float pg_rho_bar, float lambda_,
-                                   float* __restrict__ vs_out, float* __restrict__ adv_out, int vec_ok) {
-    extern __shared__ __align__(16) float smem[];
-    const int span = tr * t;  // floats per array per tile (padded to a multiple of 4 below)
-    const int span_pad = (span + 3) & ~3;
-    float* s_rho = smem;                  // reused for vs
-    float* s_disc = smem + span_pad;
-    float* s_rew = smem + 2 * span_pad;   // reused for pg_adv
-    float* s_val = smem + 3 * span_pad;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ntiles = (m + tr - 1) / tr;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b0 = tile * tr;
-        const int ntraj = min(tr, m - b0);
-        const int count = ntraj * t;
-        const size_t e0 = (size_t)b0 * t;
-        const bool v_ok = vec_ok && ((e0 & 3) == 0);
-        stage_in(s_rho, log_rho, e0, count, v_ok);
-        stage_in(s_disc, discount, e0, count, v_ok);
-        stage_in(s_rew, reward, e0, count, v_ok);
-        stage_in(s_val, value, e0, count, v_ok);
-        __syncthreads();
-        if (warp < ntraj) {
-            const int o = warp * t;
-            const float boot = __ldg(bootstrap + b0 + warp);
-            float carry = 0.f;          // acc_{s+1} entering the chunk
-            float vs_next_chunk = boot; // vs at the first step of the chunk after this one
-            for (int c0 = ((t - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-                const int s = c0 + lane;
-                const bool valid = s < t;
-                float a = 0.f, b = 0.f, v = 0.f, r = 0.f, g = 0.f, is = 0.f;
-                if (valid) {
-                    is = expf(s_rho[o + s]);
-                    g = s_disc[o + s];
-                    r = s_rew[o + s];
-                    v = s_val[o + s];
-                    const float v_next = (s == t - 1) ? boot : s_val[o + s + 1];
-                    const float rho = fminf(rho_bar, is);
-                    const float cc = lambda_ * fminf(c_bar, is);
-                    b = rho * (r + g * v_next - v);  // delta_s
-                    a = g * cc;
-                }
-                warp_reverse_linear_scan(a, b, lane);
-                const float acc = fmaf(a, carry, b);
-                const float vs = v + acc;
-                float vs_next = __shfl_down_sync(0xffffffffu, vs, 1);
-                if (lane == 31 || s == t - 1) vs_next = vs_next_chunk;
-                if (valid) {
-                    s_rho[o + s] = vs;
-                    s_rew[o + s] = fminf(pg_rho_bar, is) * (r + g * vs_next - v);
-                }
-                carry = __shfl_sync(0xffffffffu, acc, 0);
-                vs_next_chunk = __shfl_sync(0xffffffffu, vs, 0);
+template <int V>
+__global__ void __launch_bounds__(256)
+vtrace_scan_kernel(int m, int t, const float* __restrict__ log_rho, const float* __restrict__ discount,
+                   const float* __restrict__ reward, const float* __restrict__ value,
+                   const float* __restrict__ bootstrap, float rho_bar, float c_bar, float pg_rho_bar, float lambda_,
+                   float* __restrict__ vs_out, float* __restrict__ adv_out) {
+    const int lane = threadIdx.x & 31;
+    const int traj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (traj >= m) return;
+    constexpr int CH = 32 * V;
+    const size_t base = (size_t)traj * t;
+    const float boot = __ldg(bootstrap + traj);
+    float carry = 0.f;            // acc at the first step of the chunk after this one
+    float vs_next_chunk = boot;   // vs at that step
+    float v_next_chunk = boot;    // V at that step
+    ScanChunk<V> cur, nxt;
+    int c0 = ((t - 1) / CH) * CH;
+    scan_load<V>(cur, log_rho, discount, reward, value, base, c0 + lane * V, t);
+    for (; c0 >= 0; c0 -= CH) {
+        if (c0 >= CH) scan_load<V>(nxt, log_rho, discount, reward, value, base, c0 - CH + lane * V, t);
+        const int s0 = c0 + lane * V;
+        // V of the step after this lane's last one
+        float v_after = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
+        if (lane == 31) v_after = v_next_chunk;
+        float is[V], a[V], b[V];
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            const int s = s0 + e;
+            is[e] = expf(cur.lr[e]);
+            float v_next = e + 1 < V ? cur.v[e + 1] : v_after;
+            if (s >= t - 1) v_next = boot;
+            const bool valid = s < t;
+            a[e] = valid ? cur.g[e] * lambda_ * fminf(c_bar, is[e]) : 0.f;
+            b[e] = valid ? fminf(rho_bar, is[e]) * (cur.r[e] + cur.g[e] * v_next - cur.v[e]) : 0.f;  // delta_s
+        }
+        // fold the lane's V steps: acc_first = B + A * (carry into the lane)
+        float A = a[V - 1], B = b[V - 1];
+#pragma unroll
+        for (int e = V - 2; e >= 0; e--) {
+            B = fmaf(a[e], B, b[e]);
+            A *= a[e];
+        }
+        warp_reverse_linear_scan(A, B, lane);
+        const float acc_first = fmaf(A, carry, B);
+        float lane_carry = __shfl_down_sync(0xffffffffu, acc_first, 1);
+        if (lane == 31) lane_carry = carry;
+        float acc[V], vs[V];
+        float run = lane_carry;
+#pragma unroll
+        for (int e = V - 1; e >= 0; e--) {
+            run = fmaf(a[e], run, b[e]);
+            acc[e] = run;
+            vs[e] = cur.v[e] + run;
+        }
+        float vs_after = __shfl_down_sync(0xffffffffu, vs[0], 1);
+        if (lane == 31) vs_after = vs_next_chunk;
+        float adv[V];
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            const int s = s0 + e;
+            float vs_next = e + 1 < V ? vs[e + 1] : vs_after;
+            if (s >= t - 1) vs_next = boot;
+            adv[e] = fminf(pg_rho_bar, is[e]) * (cur.r[e] + cur.g[e] * vs_next - cur.v[e]);
+        }
+        bool stored = false;
+        if constexpr (V == 4) {
+            if (s0 + 3 < t) {
+                *reinterpret_cast<float4*>(vs_out + base + s0) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+                if (adv_out) *reinterpret_cast<float4*>(adv_out + base + s0) = make_float4(adv[0], adv[1], adv[2], adv[3]);
+                stored = true;
             }
         }
-        __syncthreads();
-        stage_out(vs_out, s_rho, e0, count, v_ok);
-        if (adv_out) stage_out(adv_out, s_rew, e0, count, v_ok);
-        __syncthreads();
+        if (!stored) {
+#pragma unroll
+            for (int e = 0; e < V; e++)
+                if (s0 + e < t) {
+                    vs_out[base + s0 + e] = vs[e];
+                    if (adv_out) adv_out[base + s0 + e] = adv[e];
+                }
+        }
+        carry = __shfl_sync(0xffffffffu, acc[0], 0);
+        vs_next_chunk = __shfl_sync(0xffffffffu, vs[0], 0);
+        v_next_chunk = __shfl_sync(0xffffffffu, cur.v[0], 0);
+        cur = nxt;
     }
 }
 
@@ -129,28 +162,20 @@ int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount
     if (m <= 0 || t <= 0) return FI_OK;
     if (!log_rho || !discount || !reward || !value || !bootstrap || !vs)
         return set_error(FI_ERR_ARG, "vtrace: null argument");
-    // trajectories per CTA: one warp each, at most 8, sized so that >= 2 CTAs fit one SM
-    const size_t per_traj = (size_t)16 * t;  // 4 staged arrays x 4 B
-    int tr = (int)((96 * 1024) / per_traj);
-    if (tr > 8) tr = 8;
-    if (tr < 1) tr = 1;
-    const size_t smem = 4 * (((size_t)tr * t + 3) & ~(size_t)3) * sizeof(float);
-    if (smem > 227 * 1024) return set_error(FI_ERR_ARG, "vtrace: T=%d too long for shared-memory staging", t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FI_CUDA_OK(cudaFuncSetAttribute(vtrace_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    uintptr_t al = (uintptr_t)log_rho | (uintptr_t)discount | (uintptr_t)reward | (uintptr_t)value | (uintptr_t)vs |
-                   (uintptr_t)pg_adv;
-    const int vec_ok = (al & 15) == 0;
-    const int ntiles = (m + tr - 1) / tr;
-    const int cap = kNumSMs * 16;
-    const int grid = ntiles < cap ? ntiles : cap;
+    const uintptr_t al = (uintptr_t)log_rho | (uintptr_t)discount | (uintptr_t)reward | (uintptr_t)value | (uintptr_t)vs |
+                         (uintptr_t)pg_adv;
+    // 16-byte accesses need every trajectory to start on a 16-byte boundary
+    const bool vec = (al & 15) == 0 && (t % 4) == 0 && t >= 64;
+    const int warps = 8;
+    const int grid = (m + warps - 1) / warps;
     // algorithmic traffic: 16 B in + 8 B out per transition, + 4 B per trajectory (bootstrap)
     LaunchScope ls("vtrace_scan_kernel", stream, (pg_adv ? 24.0 : 20.0) * (double)m * t + 4.0 * m, kWorkBytes);
-    vtrace_scan_kernel<<<grid, 32 * tr, smem, stream>>>(m, t, tr, log_rho, discount, reward, value, bootstrap,
-                                                         rho_bar, c_bar, pg_rho_bar, lambda_, vs, pg_adv, vec_ok);
+    if (vec)
+        vtrace_scan_kernel<4><<<grid, 32 * warps, 0, stream>>>(m, t, log_rho, discount, reward, value, bootstrap, rho_bar, c_bar,
+                                                             pg_rho_bar, lambda_, vs, pg_adv);
+    else
+        vtrace_scan_kernel<1><<<grid, 32 * warps, 0, stream>>>(m, t, log_rho, discount, reward, value, bootstrap, rho_bar, c_bar,
+                                                             pg_rho_bar, lambda_, vs, pg_adv);
     return ls.done();
 }
 
