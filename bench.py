@@ -232,10 +232,8 @@ def run_b200_arm(args):
     K, W = args.steps, max(args.warmup, 0)
     cap = 2 * M
     L = fi.Learner(1, cap, T, M, model="mlp_actor_critic", device=local, gemm_mode=args.gemm_mode, seed=1, lr=5e-4)
-    if world > 1:
-        ids = [fi.Learner.dp_create_ids(1) if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        L.dp_init(ids[0], rank, world)
+    from freeimpala_b200 import dp
+    dp.init_learner_dp(L, rank, world)
     lib = fi.load_library()
     stream_ptr = lib.fi_learner_stream(L._h, 0)
     ext = torch.cuda.ExternalStream(stream_ptr, device=torch.device("cuda", local))
