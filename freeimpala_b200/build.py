@@ -35,11 +35,12 @@ def sources() -> list[str]:
 
 
 def _deps() -> list[str]:
-    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    return (sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")) +
+            glob.glob(os.path.join(PKG, "host", "*")))
 
 
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(OUT_DIR, "freeimpala_gpu")):
         return False
     t = os.path.getmtime(LIB)
     return all(os.path.getmtime(f) <= t for f in _deps())
@@ -71,7 +72,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(LIB + ".tmp", LIB)
+    build_host()
     return LIB
+
+
+HOST_BIN = os.path.join(OUT_DIR, "freeimpala_gpu")
+
+
+def build_host() -> str:
+    """The C++ host harness above the C ABI (freeimpala_b200/host): plain g++, linked against the library."""
+    src = os.path.join(PKG, "host", "freeimpala_gpu_main.cpp")
+    cxx = next((c for c in ("/usr/bin/g++", "g++") if not os.path.isabs(c) or os.path.exists(c)), "g++")
+    r = subprocess.run([cxx, "-O2", "-std=c++17", "-pthread", "-Wall", src, "-o", HOST_BIN, "-L" + OUT_DIR,
+                        "-lfreeimpala_b200", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"host harness build failed:\n{r.stdout}\n{r.stderr}")
+    return HOST_BIN
 
 
 if __name__ == "__main__":
