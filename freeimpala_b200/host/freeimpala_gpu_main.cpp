@@ -107,6 +107,13 @@ int main(int argc, char** argv) {
         std::vector<std::thread> threads;
         for (size_t a = 0; a < P.agents; a++) threads.emplace_back([&, a] { actor(a, P, learner, inferences); });
         for (auto& t : threads) t.join();
+        // The reference stops the learner as soon as the agents have joined (main.cpp:239-246), which drops whatever
+        // the workers have not consumed yet. Every trajectory needed for learner_iterations updates has been written
+        // at this point, so let the workers finish them (bounded wait) to make the run deterministic.
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(120);
+        auto done = [&] { size_t u = 0; for (size_t p = 0; p < P.players; p++) u += learner.iterationsDone(p); return u; };
+        while (done() < learner_iterations * P.players && std::chrono::steady_clock::now() < deadline)
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
         learner.stop();
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         size_t updates = 0;
