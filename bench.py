@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU per step (M)")
     ap.add_argument("--seq", type=int, default=100, help="transitions per trajectory (T = entry size S)")
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05"])
-    ap.add_argument("--writers", type=int, default=8, help="actor threads feeding the ring in the e2e leg")
+    ap.add_argument("--writers", type=int, default=min(16, os.cpu_count() or 8), help="actor threads feeding the ring in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")

@@ -44,6 +44,7 @@ struct TcOut {
     const uint32_t* mask_bits_in;            // bit-packed ReLU decisions applied to the output (backward), or null
     uint32_t* mask_bits_out;                 // bit-packed (output > 0) written by a ReLU epilogue (forward), or null
     int mask_ldw;                            // words per mask row (a multiple of 4)
+    float* colsum_out;                       // [4 * ceil(m/128), n] per-32-row column sums of the output (split-output path), or null
 };
 int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st);
 int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,

@@ -4,22 +4,25 @@
 // TF32 / bf16 operands, so every fp32 operand x is carried as an exact pair
 //     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
 //                    lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits),
-// and each product is issued as three kind::tf32 MMAs:
-//     main += A_hi B_hi            corr += A_hi B_lo + A_lo B_hi      (A_lo B_lo ~ 2^-22 relative is dropped).
-// Measured on B200: the tensor core adds into its fp32 accumulator with truncation, ~1 ulp of the
-// running sum per MMA, biased towards zero (error grew linearly with K: 2.4e-5 at K=32, 4.6e-4 at K=512
-// on sums of magnitude ~20). The big products therefore accumulate in TMEM only over a CHUNK of 2
-// k-blocks (8 MMAs); the promotion warps then add the chunk to fp32 register accumulators with
-// round-to-nearest (the scheme of Ootomo & Yokota 2022, at chunk granularity). The correction
-// terms are 2^-11 smaller, so their own truncation is harmless and they stay in TMEM per tile.
+// and each product needs three kind::tf32 products:
+//     main += A_hi B_hi            corr += A_hi B_lo + A_lo B_hi      (A_lo B_lo ~ 2^-22 relative is dropped),
+// issued as TWO instructions per k-slice: B_hi and B_lo tiles are adjacent in shared memory, so one N = 2*BN MMA
+// computes A_hi [B_hi | B_lo] into [main | corr] (adjacent TMEM columns) and one N = BN MMA adds A_lo B_hi to corr.
+// Measured on B200: the tensor core adds into its fp32 accumulator with truncation towards zero, a few ulp
+// of the running sum per MMA (error grew linearly with K: 2.4e-5 at K=32, 4.6e-4 at K=512 on sums of
+// magnitude ~20 when one accumulator took all of K). The products therefore accumulate in TMEM only over
+// a CHUNK of 4 k-blocks (K = 128); the promotion warps then add the chunk (main + corr) to fp32 register
+// accumulators with round-to-nearest (the scheme of Ootomo & Yokota 2022, at chunk granularity): 6.5e-5 at
+// K=512 (1.7e-6 of the largest sum). Halving the chunk only gave 5.0e-5: what is left is the truncation
+// inside each MMA's own 8-term sum, which no promotion schedule removes.
 //
 // Kernel anatomy (one CTA per SM, persistent over output tiles; 256 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A_hi, A_lo, B_hi, B_lo into a
 //              multi-stage shared-memory ring, completion on mbarriers;
-//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=8) x 4 k-slices x 3 products
-//              per 32-wide k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
-//   warp 2     TMEM allocator: 2 chunk accumulators + 2 correction accumulators of BN fp32 columns each, so the
-//              promotion of chunk i overlaps the MMAs of chunk i+1 and the epilogue of tile j those of tile j+1;
+//   warp 1     MMA issuer: one elected lane issues 2 tcgen05.mma (M=128, K=8; N=2*BN and N=BN) x 4 k-slices per
+//              32-wide k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
+//   warp 2     TMEM allocator: 2 chunk buffers of [main | corr] = 2*BN fp32 columns each, so the promotion of
+//              chunk i overlaps the MMAs of chunk i+1 and the epilogue of tile j those of tile j+1;
 //   warps 4-7  promotion + epilogue: tcgen05.ld (32 lanes x 32 columns per warp) into BN register accumulators per
 //              thread, then bias / ReLU / ReLU-mask and either a plain fp32 store or the hi/lo split store that
 //              feeds the next GEMM.
@@ -38,7 +41,7 @@ namespace fi {
 constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int kTcThreads = 256;
-constexpr int kTcChunk = 2;      // k-blocks accumulated in TMEM before promotion to registers (8 main MMAs)
+constexpr int kTcChunk = 4;      // k-blocks accumulated in TMEM before promotion to registers (16 wide MMAs)
 constexpr int kTcSmemLimit = 227 * 1024;
 
 struct TcEpilogue {
@@ -56,6 +59,7 @@ struct TcEpilogue {
     int relu;
     int transpose_out;   // c[col * ldc + row] (plain output only)
     int tma_split;       // c_hi / c_lo are written with TMA stores (map_c_hi / map_c_lo are valid)
+    float* colsum_out;   // [4 * num_m_blocks, n]: column sums of the output over each warp's 32 rows (bias gradient), or null
     size_t split_stride; // elements between split-K slabs of c
 };
 
@@ -154,7 +158,7 @@ struct TcCfg {
     static constexpr int kStageBytes = 2 * (kTcBM + BN) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static constexpr int kStages = BN >= 128 ? 3 : 4;
-    static constexpr int kTmemCols = 4 * BN;                          // main[2] + corr[2] (a power of two >= 32)
+    static constexpr int kTmemCols = 4 * BN;                          // 2 chunk buffers x [main | corr] (a power of two >= 32)
     static constexpr int kOutTileBytes = 4 * 2 * 32 * 128;            // per epilogue warp: hi + lo staging tiles of 32 x 128 B
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
@@ -174,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     constexpr uint32_t kBoxBytes = 32 * kTcBK * 4;    // one MN-major box: 32 k-rows x 128 B
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
-    // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2], corr_empty[2]
+    // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2]
     const uint32_t out_tiles = smem_base + kStages * Cfg::kStageBytes;    // 1024-byte aligned: TMA-store staging, 8 KB per warp
     const uint32_t bar_base = out_tiles + Cfg::kOutTileBytes;
     const uint32_t tmem_slot = bar_base + (2 * kStages + 6) * 8;
@@ -182,7 +186,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto main_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
     auto main_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-    auto corr_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 4 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = sh.num_m_blocks * sh.num_n_blocks;
@@ -196,7 +199,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int s = 0; s < 2; s++) {
             mbar_init(main_full_bar(s), 1);
             mbar_init(main_empty_bar(s), 4);  // one arrival per promotion warp
-            mbar_init(corr_empty_bar(s), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -210,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-    // TMEM columns: main chunk accumulators at [0, BN) and [BN, 2BN); correction accumulators at [2BN, 3BN), [3BN, 4BN)
+    // TMEM columns of chunk buffer b: main at [2b*BN, 2b*BN + BN), corr at [2b*BN + BN, 2b*BN + 2BN)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -255,55 +257,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kTcBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint32_t idesc_wide = umma_idesc(kTcBM, 2 * BN, A_MN ? 1 : 0, B_MN ? 1 : 0);  // A_hi [B_hi | B_lo]
+            constexpr uint32_t idesc_half = umma_idesc(kTcBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);       // A_lo B_hi
             // K-major (128B swizzle, 16 B atoms): a k-slice of 8 fp32 is 32 bytes inside the 128-byte row; 8-row groups
             // are 1024 B apart (SBO). MN-major (128B swizzle, 32 B atoms): a k-slice is 8 rows of 128 B = two 4-row
-            // atoms 512 B apart (SBO); 32-wide MN blocks are one TMA box (4096 B) apart (LBO).
-            constexpr uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+            // atoms 512 B apart (SBO); 32-wide MN blocks are one TMA box (4096 B) apart (LBO). The B_lo tile follows
+            // the B_hi tile with the same strides, so a descriptor at B_hi with N = 2*BN covers both.
+            constexpr uint32_t a_step = (A_MN ? 1024u : 32u) >> 4, b_step = (B_MN ? 1024u : 32u) >> 4;
             constexpr uint32_t a_lbo = A_MN ? kBoxBytes : 0u, b_lbo = B_MN ? kBoxBytes : 0u;
             constexpr uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
-            constexpr uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
-            int stage = 0, mb = 0, cb = 0;
-            uint32_t phase = 0, mphase = 0, cphase = 0;
+            // descriptor words that never change: [32,46) SBO, [46,48) version 1, [61,64) layout type
+            constexpr uint32_t a_hi_word = (a_sbo >> 4) | (1u << 14) | ((A_MN ? 1u : 2u) << 29);
+            constexpr uint32_t b_hi_word = (b_sbo >> 4) | (1u << 14) | ((B_MN ? 1u : 2u) << 29);
+            auto desc = [](uint32_t hi_word, uint32_t lo_word) { return ((uint64_t)hi_word << 32) | lo_word; };
+            int stage = 0, mb = 0;
+            uint32_t phase = 0, mphase = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
-                mbar_wait(corr_empty_bar(cb), cphase ^ 1);
-                const uint32_t tmem_corr = tmem_base + (uint32_t)((2 + cb) * BN);
                 for (int kc = kb0; kc < kb1; kc += kTcChunk) {
                     mbar_wait(main_empty_bar(mb), mphase ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_main = tmem_base + (uint32_t)(mb * BN);
+                    const uint32_t tmem_main = tmem_base + (uint32_t)(mb * 2 * BN), tmem_corr = tmem_main + BN;
                     const int kce = min(kb1, kc + kTcChunk);
                     for (int kb = kc; kb < kce; kb++) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
-                        const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
+                        const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes, b_hi = a_lo + kABytes;
+                        // low descriptor words: [0,14) start address >> 4, [16,30) LBO >> 4
+                        const uint32_t la_hi = ((a_hi >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+                        const uint32_t la_lo = ((a_lo >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+                        const uint32_t lb_hi = ((b_hi >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
 #pragma unroll
                         for (int ks = 0; ks < kTcBK / 8; ks++) {
-                            const uint64_t da_hi = umma_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
-                            const uint64_t da_lo = umma_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
-                            const uint64_t db_hi = umma_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
-                            const uint64_t db_lo = umma_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-                            tc_mma_tf32(tmem_main, da_hi, db_hi, idesc, (kb > kc || ks > 0) ? 1u : 0u);
-                            tc_mma_tf32(tmem_corr, da_hi, db_lo, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-                            tc_mma_tf32(tmem_corr, da_lo, db_hi, idesc, 1u);
+                            const uint64_t da_hi = desc(a_hi_word, la_hi + ks * a_step);
+                            const uint64_t da_lo = desc(a_hi_word, la_lo + ks * a_step);
+                            const uint64_t db = desc(b_hi_word, lb_hi + ks * b_step);
+                            tc_mma_tf32(tmem_main, da_hi, db, idesc_wide, (kb > kc || ks > 0) ? 1u : 0u);  // [main | corr] (+)= A_hi [B_hi | B_lo]
+                            tc_mma_tf32(tmem_corr, da_lo, db, idesc_half, 1u);                             // corr += A_lo B_hi
                         }
                         tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(main_full_bar(mb));     // chunk complete (and, for the last chunk, the tile's corrections)
+                    tc_commit(main_full_bar(mb));     // chunk complete
                     if (++mb == 2) { mb = 0; mphase ^= 1; }
                 }
-                if (++cb == 2) { cb = 0; cphase ^= 1; }
             }
         }
     } else if (warp >= 4) {
         // ===================== promotion + epilogue =====================
         const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        int mb = 0, cb = 0;
+        int mb = 0;
         uint32_t mphase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int tile = w % tiles, split = w / tiles;
@@ -329,30 +334,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < BN / 32; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * BN + c * 32), v);
+                    uint32_t v[32], u[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + c * 32), v);       // main
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + c * 32), u);  // corr
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i++) acc[c * 32 + i] += __uint_as_float(v[i]);  // round-to-nearest promotion
+                    for (int i = 0; i < 32; i++)  // round-to-nearest promotion
+                        acc[c * 32 + i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(main_empty_bar(mb));
                 if (++mb == 2) { mb = 0; mphase ^= 1; }
             }
-            // the last chunk's commit also covers this tile's correction MMAs
-#pragma unroll
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + (uint32_t)((2 + cb) * BN + c * 32), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i++) acc[c * 32 + i] += __uint_as_float(v[i]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(corr_empty_bar(cb));
-            cb ^= 1;
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
             if (ep.transpose_out) {
                 // c[col * ldc + row]: lanes hold consecutive rows, so the register layout is already coalesced
@@ -412,6 +406,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         st_shared_v4(out_lo + off, l);
                     }
                     if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
+                    if (ep.colsum_out) {
+                        // column sums over this warp's 32 rows by recursive halving: after the step with offset o a lane keeps
+                        // the half of its columns selected by its bit o, summed with its partner's; 31 shuffles, and lane j
+                        // ends up with the sum of column j. Rows beyond m contribute exact zeros (zero-filled A rows).
+                        float y16[16], y8[8], y4[4], y2[2];
+                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float lo_v = acc[c * 32 + i], hi_v = acc[c * 32 + 16 + i];
+                            y16[i] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xFFFFFFFFu, b16 ? lo_v : hi_v, 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) y8[i] = (b8 ? y16[8 + i] : y16[i]) + __shfl_xor_sync(0xFFFFFFFFu, b8 ? y16[i] : y16[8 + i], 8);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) y4[i] = (b4 ? y8[4 + i] : y8[i]) + __shfl_xor_sync(0xFFFFFFFFu, b4 ? y8[i] : y8[4 + i], 4);
+#pragma unroll
+                        for (int i = 0; i < 2; i++) y2[i] = (b2 ? y4[2 + i] : y4[i]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? y4[i] : y4[2 + i], 2);
+                        const float y1 = (b1 ? y2[1] : y2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? y2[0] : y2[1], 1);
+                        if (col0 + lane < sh.n)
+                            ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
                     __syncwarp();
                     if (lane == 0) {
@@ -607,6 +622,8 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
     ep.mask_bits = out.mask_bits_in; ep.mask_bits_out = out.mask_bits_out; ep.mask_ldw = out.mask_ldw;
+    ep.colsum_out = out.colsum_out;
+    if (ep.colsum_out && (bias || relu)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: fused column sums exclude bias/ReLU");
     if (ep.mask_bits && (bias || relu || (n > 32 && (ep.mask_ldw % 4 || (reinterpret_cast<uintptr_t>(ep.mask_bits) & 15)))))
         return set_error(FI_ERR_ARG, "tcgen05 GEMM: a bit mask excludes bias/ReLU and needs 16-byte aligned rows");
     if (sh.num_splits > 1) {
@@ -646,6 +663,7 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     } else {
         maps[4] = maps[0];
         maps[5] = maps[0];
+        if (ep.colsum_out) return set_error(FI_ERR_ARG, "tcgen05 GEMM: fused column sums need the TMA split-output path");
     }
     const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
@@ -701,7 +719,7 @@ int launch_gemm_tc(int trans, int m, int n, int k, const float* a, int lda, cons
     FI_TRY(launch_split_tf32(a, lda, a_rows, (int)a_cols, (int)a_ld, a_hi, a_lo, st));
     FI_TRY(launch_split_tf32(b, ldb, b_rows, (int)b_cols, (int)b_ld, b_hi, b_lo, st));
     SplitMat sa{a_hi, a_lo, (int)a_ld}, sb{b_hi, b_lo, (int)b_ld};
-    TcOut out{c, ldc, nullptr, nullptr, 0, 0, nullptr, nullptr, 0};
+    TcOut out{c, ldc, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
     const size_t split_ws = gemm_tc_split_workspace_bytes(trans, m, n, k);
     if (trans == 2 && ldc != n) {  // split-K partials need a dense output
         return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, nullptr, 0, st);

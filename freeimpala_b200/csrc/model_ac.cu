@@ -27,6 +27,7 @@ struct AcTc {  // tensor-core path state, owned by the Player (Player::ac_tc)
     float* d_lo[2] = {nullptr, nullptr};
     float *dhead_hi = nullptr, *dhead_lo = nullptr;  // [rows, 32], columns 17..31 stay zero
     uint32_t* relu_bits[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [rows, 16] words: act_l > 0, bit-packed
+    float* colsum_part = nullptr;                    // [4 * ceil(rows/128), 512]: per-warp column sums from the dgrad epilogue
     void* ws = nullptr; size_t ws_bytes = 0;         // split-K partials
 };
 
@@ -62,6 +63,7 @@ int ac_alloc(fi_learner* l, Player* p) {
         FI_CUDA_OK(cudaMalloc((void**)&t->dhead_lo, rows * kDheadLd * sizeof(float)));
         FI_CUDA_OK(cudaMemset(t->dhead_hi, 0, rows * kDheadLd * sizeof(float)));
         FI_CUDA_OK(cudaMemset(t->dhead_lo, 0, rows * kDheadLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->colsum_part, 4 * ((rows + 127) / 128) * kHid * sizeof(float)));
         size_t ws = 0;
         auto upd = [&](size_t b) { if (b > ws) ws = b; };
         upd(gemm_tc_split_workspace_bytes(2, kHid, kZDim, (int)rows));
@@ -87,7 +89,7 @@ void ac_free(Player* p) {
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.clear();
     if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
-        float* f[] = {t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
+        float* f[] = {t->colsum_part, t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
                       t->d_hi[1], t->d_lo[0], t->d_lo[1]};
         for (float* x : f) if (x) cudaFree(x);
         for (int i = 0; i < 5; i++) {
@@ -182,11 +184,11 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     for (int layer = 0; layer < 5; layer++) {
         const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
         const SplitMat w = layer == 0 ? w1 : W(2 * layer, kHid);
-        const TcOut out{nullptr, 0, tc->act_hi[layer], tc->act_lo[layer], kHid, 0, nullptr, tc->relu_bits[layer], kHid / 32};
+        const TcOut out{nullptr, 0, tc->act_hi[layer], tc->act_lo[layer], kHid, 0, nullptr, tc->relu_bits[layer], kHid / 32, nullptr};
         FI_TRY(launch_gemm_tc_split(0, rows, kHid, layer == 0 ? kZDim : kHid, x, w, out, p->params + T[2 * layer + 1].offset, 1,
                                     nullptr, 0, nullptr, 0, st));
     }
-    FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0},
+    FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
                                 p->params + T[11].offset, 0, nullptr, 0, nullptr, 0, st));
     FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
     FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
@@ -196,23 +198,25 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     // head: db = colsum(dhead); dWh^T [512,17] = act4^T dhead, stored transposed as dWh [17,512];
     // d4 = (dhead Wh) * relu'(act4)
     FI_TRY(launch_colsum2(tc->dhead_hi, tc->dhead_lo, kDheadLd, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
-    FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, TcOut{g + T[10].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0}, nullptr,
+    FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, TcOut{g + T[10].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, nullptr}, nullptr,
                                 0, nullptr, 0, tc->ws, tc->ws_bytes, st));
     int cur = 0;
     FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHead, dhead, W(10, kHid),
-                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32}, nullptr, 0,
+                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32, tc->colsum_part}, nullptr, 0,
                                 nullptr, 0, nullptr, 0, st));
     for (int layer = 4; layer >= 0; layer--) {
         const SplitMat d{tc->d_hi[cur], tc->d_lo[cur], kHid};
         const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
         const int k = layer == 0 ? kZDim : kHid;
-        FI_TRY(launch_colsum2(d.hi, d.lo, kHid, rows, kHid, g + T[2 * layer + 1].offset, p->colsum_ws, p->colsum_ws_bytes, st));
-        FI_TRY(launch_gemm_tc_split(2, kHid, k, rows, d, x, TcOut{g + T[2 * layer].offset, k, nullptr, nullptr, 0, 0, nullptr, nullptr, 0}, nullptr, 0,
+        // bias gradient: the dgrad epilogue that produced d left per-32-row column sums (6.5 MB instead of re-reading 420 MB)
+        FI_TRY(launch_colsum(tc->colsum_part, kHid, 4 * ((rows + 127) / 128), kHid, g + T[2 * layer + 1].offset, p->colsum_ws,
+                             p->colsum_ws_bytes, st));
+        FI_TRY(launch_gemm_tc_split(2, kHid, k, rows, d, x, TcOut{g + T[2 * layer].offset, k, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr}, nullptr, 0,
                                     nullptr, 0, tc->ws, tc->ws_bytes, st));
         if (layer > 0) {
             FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHid, d, W(2 * layer, kHid),
                                         TcOut{nullptr, 0, tc->d_hi[cur ^ 1], tc->d_lo[cur ^ 1], kHid, 0, tc->relu_bits[layer - 1], nullptr,
-                                              kHid / 32},
+                                              kHid / 32, tc->colsum_part},
                                         nullptr, 0, nullptr, 0, nullptr, 0, st));
             cur ^= 1;
         }
