@@ -5,8 +5,9 @@
 // pinned host memory mirrored by `capacity` slots in HBM. A writer reserves a slot under the
 // lock, copies its bytes into the pinned slot OUTSIDE the lock (the reference copies 100 KiB
 // under the mutex, data_structures.h:226-227, serialising every actor), and commits; commits
-// are published in reservation order and each enqueues cudaMemcpyAsync(pinned -> HBM slot) on
-// the ring's side stream. readBatch (:267-300) becomes one sm_100a kernel that gathers M
+// are published in reservation order; runs of consecutive committed slots go to HBM with ONE
+// cudaMemcpyAsync per run on the ring's side stream (a copy per slot put ~5 us of driver calls per
+// trajectory under the ring lock: 1024 writes per step cost more than the learner step itself). readBatch (:267-300) becomes one sm_100a kernel that gathers M
 // consecutive HBM slots (FIFO, wraparound) into a contiguous [M, slot_bytes] batch.
 #include <condition_variable>
 #include <mutex>
@@ -77,7 +78,10 @@ struct fi_ring {
     size_t batch_cap = 0;
     cudaStream_t side = nullptr;     // H2D copies
     cudaStream_t learner = nullptr;  // default stream for the gather
-    std::vector<cudaEvent_t> h2d_done;  // per slot: its last H2D has completed
+    std::vector<cudaEvent_t> h2d_done;  // per slot: recorded after the H2D run that ENDS at this slot
+    std::vector<size_t> h2d_ref;        // per slot: the slot whose event covers this slot's last H2D
+    cudaEvent_t h2d_tail = nullptr;     // recorded after the most recent H2D run (covers all earlier ones)
+    size_t copy_index = 0, uncopied = 0;  // published slots [copy_index, copy_index + uncopied) are not in HBM yet
     std::vector<unsigned char> committed;  // per slot: writer finished filling the pinned slot
     std::vector<size_t> commit_bytes;
     cudaEvent_t gather_done = nullptr;  // last gather has finished reading the HBM slots
@@ -130,6 +134,9 @@ fi_ring* fi_ring_create(int device, size_t entry_size, size_t capacity) {
     for (size_t i = 0; i < capacity; i++)
         if ((e = cudaEventCreateWithFlags(&r->h2d_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&r->gather_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&r->h2d_tail, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    r->h2d_ref.resize(capacity);
+    for (size_t i = 0; i < capacity; i++) r->h2d_ref[i] = i;
     r->committed.assign(capacity, 0);
     r->commit_bytes.assign(capacity, 0);
     return r;
@@ -143,6 +150,7 @@ void fi_ring_destroy(fi_ring* r) {
     for (auto ev : r->h2d_done)
         if (ev) cudaEventDestroy(ev);
     if (r->gather_done) cudaEventDestroy(r->gather_done);
+    if (r->h2d_tail) cudaEventDestroy(r->h2d_tail);
     if (r->side) cudaStreamDestroy(r->side);
     if (r->learner) cudaStreamDestroy(r->learner);
     if (r->dev_batch) cudaFree(r->dev_batch);
@@ -151,29 +159,71 @@ void fi_ring_destroy(fi_ring* r) {
     delete r;
 }
 
+constexpr size_t kH2DRunSlots = 32;                 // copy once this many published slots are waiting ...
+constexpr size_t kH2DRunBytes = (size_t)4 << 20;    // ... or this many bytes, whichever comes first
+
+// Copy published-but-uncopied slots to HBM: one cudaMemcpyAsync per run of consecutive full slots (a short
+// write copies only its own bytes, data_structures.h:226-227). Caller holds r->mu.
+static void ring_flush_locked(fi_ring* r, bool force) {
+    if (r->uncopied == 0) return;
+    if (!force && r->uncopied < kH2DRunSlots && r->uncopied * r->slot_bytes < kH2DRunBytes) return;
+    if (r->gather_pending) {  // the HBM slots may still be being read by the last gather
+        cudaStreamWaitEvent(r->side, r->gather_done, 0);
+        r->gather_pending = false;  // the side stream is ordered behind it from now on
+    }
+    cudaError_t e = cudaSuccess;
+    while (r->uncopied > 0 && e == cudaSuccess) {
+        const size_t first = r->copy_index;
+        size_t len = 0, bytes = 0;
+        // a run: consecutive slots up to the ring end; a partially written slot ends the run after itself
+        while (len < r->uncopied && first + len < r->capacity) {
+            const size_t n = r->commit_bytes[first + len];
+            len++;
+            if (n != r->slot_bytes) { bytes = n; break; }
+            bytes = 0;
+        }
+        const size_t full = (bytes == 0 && r->commit_bytes[first + len - 1] == r->slot_bytes) ? len : len - 1;
+        if (full > 0)
+            e = cudaMemcpyAsync(r->dev_slots + first * r->slot_bytes, r->host_slots + first * r->slot_bytes,
+                                full * r->slot_bytes, cudaMemcpyHostToDevice, r->side);
+        if (e == cudaSuccess && full < len && bytes > 0)
+            e = cudaMemcpyAsync(r->dev_slots + (first + full) * r->slot_bytes, r->host_slots + (first + full) * r->slot_bytes,
+                                bytes, cudaMemcpyHostToDevice, r->side);
+        const size_t last = first + len - 1;
+        if (e == cudaSuccess) e = cudaEventRecord(r->h2d_done[last], r->side);
+        for (size_t i = first; i <= last; i++) r->h2d_ref[i] = last;
+        r->copy_index = (last + 1) % r->capacity;
+        r->uncopied -= len;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(r->h2d_tail, r->side);
+    if (e != cudaSuccess) set_error(FI_ERR_CUDA, "fi_ring_write: H2D failed: %s", cudaGetErrorString(e));
+}
+
 // Publish committed slots in reservation order. Caller holds r->mu.
 static int ring_publish_locked(fi_ring* r) {
     int published = 0;
     while (r->reserved > 0 && r->committed[r->commit_index]) {
-        const size_t i = r->commit_index, n = r->commit_bytes[i];
-        if (r->gather_pending) {  // the HBM slot may still be being read by the last gather
-            cudaStreamWaitEvent(r->side, r->gather_done, 0);
-            r->gather_pending = false;  // side stream is ordered behind it from now on
-        }
-        cudaError_t e = cudaSuccess;
-        if (n > 0)
-            e = cudaMemcpyAsync(r->dev_slots + i * r->slot_bytes, r->host_slots + i * r->slot_bytes, n,
-                                cudaMemcpyHostToDevice, r->side);
-        // recorded even for an empty write: readBatch waits on the newest slot's event only
-        if (e == cudaSuccess) e = cudaEventRecord(r->h2d_done[i], r->side);
-        if (e != cudaSuccess) set_error(FI_ERR_CUDA, "fi_ring_write: H2D of slot %zu failed: %s", i, cudaGetErrorString(e));
+        const size_t i = r->commit_index;
         r->committed[i] = 0;
         r->commit_index = (i + 1) % r->capacity;
         r->reserved--;
         r->count++;
+        r->uncopied++;
         published++;
     }
+    if (published) ring_flush_locked(r, false);
     return published;
+}
+
+// Block until the previous occupant of a pinned slot has reached HBM (the slot was consumed by readBatch before it
+// could be reserved again, and readBatch flushes every pending copy, so the covering event has been recorded).
+static void ring_wait_slot_copied(fi_ring* r, size_t slot) {
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lock(r->mu);
+        ev = r->h2d_done[r->h2d_ref[slot]];
+    }
+    cudaEventSynchronize(ev);
 }
 
 static void* ring_reserve_locked(fi_ring* r, std::unique_lock<std::mutex>& lock, uint64_t* ticket, size_t* slot) {
@@ -215,7 +265,7 @@ static int ring_write_impl(fi_ring* r, const void* src, size_t n, bool blocking)
     }
     // The pinned slot may still be the source of an in-flight H2D from its previous occupant.
     cudaSetDevice(r->device);
-    cudaEventSynchronize(r->h2d_done[slot]);
+    ring_wait_slot_copied(r, slot);
     if (n) memcpy(r->host_slots + slot * r->slot_bytes, src, n);  // bytes [n, slot) keep old content
     return ring_commit(r, slot, n);
 }
@@ -239,7 +289,7 @@ void* fi_ring_reserve(fi_ring* r, uint64_t* ticket) {
         p = ring_reserve_locked(r, lock, ticket, &slot);
     }
     cudaSetDevice(r->device);
-    cudaEventSynchronize(r->h2d_done[slot]);
+    ring_wait_slot_copied(r, slot);
     return p;
 }
 
@@ -271,8 +321,9 @@ int fi_ring_read_batch(fi_ring* r, size_t batch_size, void* stream, fi_batch* ou
         r->batch_cap = batch_size;
     }
     const size_t first = r->read_index, last = (first + batch_size - 1) % r->capacity;
-    // H2D copies are issued in FIFO order on one stream: the newest consumed slot covers all.
-    FI_CUDA_OK(cudaStreamWaitEvent(st, r->h2d_done[last], 0));
+    // every published slot goes to HBM now; copies are issued in FIFO order on one stream, so the tail event covers all
+    ring_flush_locked(r, true);
+    FI_CUDA_OK(cudaStreamWaitEvent(st, r->h2d_tail, 0));
     FI_TRY(fi::launch_gather(r->dev_slots, r->capacity, r->slot_bytes, first, batch_size, r->dev_batch, st));
     FI_CUDA_OK(cudaEventRecord(r->gather_done, st));
     r->gather_pending = true;
