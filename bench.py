@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU per step (M)")
     ap.add_argument("--seq", type=int, default=100, help="transitions per trajectory (T = entry size S)")
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--workload", default="vtrace", choices=["vtrace", "farmer"],
+                    help="vtrace: MLP actor-critic V-trace step (headline); farmer: the reference's FarmerLstm/MSE/Adam step")
     ap.add_argument("--writers", type=int, default=min(16, os.cpu_count() or 8), help="actor threads feeding the ring in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,7 +233,9 @@ def run_b200_arm(args):
     slot_bytes = T * 1024
     K, W = args.steps, max(args.warmup, 0)
     cap = 2 * M
-    L = fi.Learner(1, cap, T, M, model="mlp_actor_critic", device=local, gemm_mode=args.gemm_mode, seed=1, lr=5e-4)
+    farmer = args.workload == "farmer"
+    L = fi.Learner(1, cap, T, M, model="farmer_lstm" if farmer else "mlp_actor_critic", device=local,
+                   gemm_mode=args.gemm_mode, seed=1, lr=5e-4)
     from freeimpala_b200 import dp
     dp.init_learner_dp(L, rank, world)
     lib = fi.load_library()
@@ -241,8 +245,8 @@ def run_b200_arm(args):
     # two distinct synthetic batches per rank, in pinned host memory and (for `value`) in an HBM ring
     host_ptr = lib.fi_host_alloc(cap * slot_bytes)
     host = np.ctypeslib.as_array((C.c_uint8 * (cap * slot_bytes)).from_address(host_ptr)).reshape(cap, slot_bytes)
-    host[:M] = synth_slots(1000 + rank, M, T)
-    host[M:] = synth_slots(2000 + rank, M, T)
+    host[:M] = synth_slots(1000 + rank, M, T)   # z / obs ~ N(0,1) in words 0..161 of every record for both workloads;
+    host[M:] = synth_slots(2000 + rank, M, T)   # the farmer step also reads x (words 192..255, zeros here) and the target
     ring_dev = torch.empty((cap, slot_bytes), dtype=torch.uint8, device="cuda")
     ring_dev.copy_(torch.from_numpy(host))
     batch_dev = torch.empty((M, slot_bytes), dtype=torch.uint8, device="cuda")
@@ -355,8 +359,16 @@ def run_b200_arm(args):
     roofline = None
     if dominant:
         d = kernels[dominant]
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
+        if os.path.exists(tpath) and not farmer:
+            tj = json.load(open(tpath))
+            key = next((k for k in tj if k.startswith(dominant) and "BN=128" in k), None)
+            if key:
+                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], f"profiles/r1_gemm_tc.md ({key}, big-layer launches)"
         roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
                     "note": "tensor peak = cuBLAS bf16 sustained; this kernel computes fp32-accurate products "
                             "(3xTF32 on tcgen05 or fp32 FFMA), whose ceiling is <= 1/6 of the bf16 peak"
                             if d["bound"] == "tensor" else "HBM copy peak"}
@@ -377,13 +389,14 @@ def run_b200_arm(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"vtrace_mlp_actor_critic learner step, batch {M} x T={T} per GPU "
-                                      f"(BASELINE.json configs[3]; records of 1024 B)",
+               "config": {"workload": (f"farmer_lstm MSE/Adam learner step (the reference's train_step), batch {M} x T={T} per GPU"
+                                       if farmer else f"vtrace_mlp_actor_critic learner step, batch {M} x T={T} per GPU "
+                                                      f"(BASELINE.json configs[3]; records of 1024 B)"),
                           "batch_per_gpu": M, "global_batch": M * world, "seq_len": T, "params": L.param_count,
                           "optimizer": "adam lr 5e-4", "gemm_mode": args.gemm_mode,
                           "parallelism": f"dp{world} (batch sharded, NCCL sum-allreduce of the flat gradient arena)",
                           "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
-                          "flops_per_step": 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
+                          "flops_per_step": None if farmer else 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
                "cpu_baseline": cpu, "losses_last_step": [float(x) for x in losses]}
         print(json.dumps(out), flush=True)
