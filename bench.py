@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--workload", default="vtrace", choices=["vtrace", "farmer"],
                     help="vtrace: MLP actor-critic V-trace step (headline); farmer: the reference's FarmerLstm/MSE/Adam step")
-    ap.add_argument("--writers", type=int, default=min(16, os.cpu_count() or 8), help="actor threads feeding the ring in the e2e leg")
+    ap.add_argument("--writers", type=int, default=0, help="actor threads feeding the ring in the e2e leg (0: min(16, host cores / ranks))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
@@ -295,7 +295,7 @@ def run_b200_arm(args):
     e2e = None
     if not args.no_e2e:
         ring = L.getSharedBuffers()[0]
-        nw = max(1, args.writers)
+        nw = args.writers if args.writers > 0 else max(2, min(16, (os.cpu_count() or 8) // world))
 
         per = (M + nw - 1) // nw
 

@@ -17,7 +17,7 @@ namespace fi {
 constexpr int kG4 = 4 * kLstmH;          // 512 gate columns
 constexpr int kFeat = kLstmH + kXDim;    // 612 = cat(h_last, x)
 constexpr int kLstmRows = 8;             // batch rows per CTA in the recurrent kernels
-constexpr int kLstmThreads = 512;
+constexpr int kLstmThreads = 256;
 
 struct FarmerWs {
     float* gates = nullptr;   // [rows*T, 512]: x-projection -> post-activation gates -> gate gradients
@@ -63,80 +63,115 @@ __global__ void farmer_assemble_dense_kernel(const float* __restrict__ x, int m,
     for (int j = threadIdx.x; j < kXDim; j += blockDim.x) feat[(size_t)b * kFeat + kLstmH + j] = __ldg(x + (size_t)b * kXDim + j);
 }
 
-// Forward recurrence. gates[(b,t), 512] holds W_ih z + b_ih on entry and the post-activation
-// gates i,f,g,o on exit. Thread j owns gate column j; each CTA owns kLstmRows batch rows.
-__global__ void __launch_bounds__(kLstmThreads)
+// Forward recurrence. gates[(b,t), 512] holds W_ih z + b_ih on entry and the post-activation gates i,f,g,o on
+// exit. Each CTA owns kLstmRows batch rows for all T steps (rows are independent: no inter-CTA synchronisation).
+// Per step the [8 x 128] x [128 x 512] product is register-tiled: thread t owns gate columns 2t, 2t+1 for all 8
+// rows (16 accumulators), reads h_{s-1} as two broadcast 16-byte shared-memory loads per k and the two weights as
+// one 8-byte load; the first 64 k-rows of W_hh^T (128 KB) stay in shared memory for the whole kernel, the other
+// half streams from L2. (The first version gave one column to each of 512 threads and re-read h with 1024
+// scalar broadcast loads per thread and step: shared-memory-issue bound at 10 us per step.)
+constexpr int kLstmSmemK = 64;  // k-rows of W_hh^T kept in shared memory
+constexpr size_t kLstmFwdSmem = ((size_t)kLstmSmemK * kG4 + kLstmRows * kG4 + kLstmH * kLstmRows + kLstmRows * kLstmH) * sizeof(float);
+
+__global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, const float* __restrict__ b_hh,
                     int m, int t, float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ feat) {
-    __shared__ float hs[kLstmRows][kLstmH];
-    __shared__ float cs[kLstmRows][kLstmH];
-    __shared__ float ps[kLstmRows][kG4];
-    const int j = threadIdx.x;
+    extern __shared__ __align__(16) float lstm_smem[];
+    float* Ws = lstm_smem;                          // [64][512]   W_hh^T rows k < 64
+    float* ps = Ws + kLstmSmemK * kG4;              // [8][512]    pre-activations of this step
+    float* hs = ps + kLstmRows * kG4;               // [128][8]    h_{s-1}, k-major
+    float* cs = hs + kLstmH * kLstmRows;            // [8][128]    c_{s-1}
+    const int tid = threadIdx.x;
+    const int j0 = 2 * tid;
     const int b0 = blockIdx.x * kLstmRows;
     const int nrows = min(kLstmRows, m - b0);
-    for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) {
-        hs[i / kLstmH][i % kLstmH] = 0.f;
-        cs[i / kLstmH][i % kLstmH] = 0.f;
-    }
-    const float bias = __ldg(b_hh + j);
+    for (int i = tid; i < kLstmSmemK * kG4 / 4; i += kLstmThreads)
+        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(whh_t) + i);
+    for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) { hs[i] = 0.f; cs[i] = 0.f; }
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(b_hh + j0));
     __syncthreads();
     for (int s = 0; s < t; s++) {
-        float acc[kLstmRows];
+        float acc[kLstmRows][2];
 #pragma unroll
-        for (int r = 0; r < kLstmRows; r++)
-            acc[r] = r < nrows ? gates[((size_t)(b0 + r) * t + s) * kG4 + j] + bias : 0.f;
-#pragma unroll 8
-        for (int k = 0; k < kLstmH; k++) {
-            const float w = __ldg(whh_t + k * kG4 + j);
-#pragma unroll
-            for (int r = 0; r < kLstmRows; r++) acc[r] = fmaf(hs[r][k], w, acc[r]);
+        for (int r = 0; r < kLstmRows; r++) {
+            float2 g = make_float2(0.f, 0.f);
+            if (r < nrows) g = *reinterpret_cast<const float2*>(gates + ((size_t)(b0 + r) * t + s) * kG4 + j0);
+            acc[r][0] = g.x + bias.x;
+            acc[r][1] = g.y + bias.y;
         }
+        auto fma_k = [&](int k, float2 w) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hs + k * kLstmRows);
+            const float4 h1 = *reinterpret_cast<const float4*>(hs + k * kLstmRows + 4);
+            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-        for (int r = 0; r < kLstmRows; r++) ps[r][j] = acc[r];
+            for (int r = 0; r < kLstmRows; r++) {
+                acc[r][0] = fmaf(hv[r], w.x, acc[r][0]);
+                acc[r][1] = fmaf(hv[r], w.y, acc[r][1]);
+            }
+        };
+#pragma unroll 8
+        for (int k = 0; k < kLstmSmemK; k++) fma_k(k, *reinterpret_cast<const float2*>(Ws + k * kG4 + j0));
+#pragma unroll 8
+        for (int k = kLstmSmemK; k < kLstmH; k++) fma_k(k, __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)k * kG4 + j0)));
+#pragma unroll
+        for (int r = 0; r < kLstmRows; r++) *reinterpret_cast<float2*>(ps + r * kG4 + j0) = make_float2(acc[r][0], acc[r][1]);
         __syncthreads();
-        // (row, unit) pairs: kLstmRows * 128 = 1024 over 512 threads
-        for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) {
+        // (row, unit) pairs: 8 * 128 = 1024 over 256 threads
+        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
             const int r = i / kLstmH, u = i % kLstmH;
+            float h = 0.f;
             if (r < nrows) {
-                const float ig = sigmoidf_(ps[r][u]), fg = sigmoidf_(ps[r][kLstmH + u]);
-                const float gg = tanhf(ps[r][2 * kLstmH + u]), og = sigmoidf_(ps[r][3 * kLstmH + u]);
-                const float c = fmaf(fg, cs[r][u], ig * gg);
-                const float h = og * tanhf(c);
+                const float ig = sigmoidf_(ps[r * kG4 + u]), fg = sigmoidf_(ps[r * kG4 + kLstmH + u]);
+                const float gg = tanhf(ps[r * kG4 + 2 * kLstmH + u]), og = sigmoidf_(ps[r * kG4 + 3 * kLstmH + u]);
+                const float c = fmaf(fg, cs[r * kLstmH + u], ig * gg);
+                h = og * tanhf(c);
                 const size_t row = (size_t)(b0 + r) * t + s;
                 float* g = gates + row * kG4;
                 g[u] = ig; g[kLstmH + u] = fg; g[2 * kLstmH + u] = gg; g[3 * kLstmH + u] = og;
                 if (cst) cst[row * kLstmH + u] = c;
-                if (hprev) hprev[row * kLstmH + u] = hs[r][u];   // h_{s-1}
-                cs[r][u] = c;
-                ps[r][u] = h;  // parked: hs is still being read as h_{s-1} by other pairs of this pass
+                if (hprev) hprev[row * kLstmH + u] = hs[u * kLstmRows + r];   // h_{s-1}
+                cs[r * kLstmH + u] = c;
                 if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = h;
             }
+            ps[r * kG4 + u] = h;  // parked: hs is still being read as h_{s-1} by other pairs of this pass
         }
         __syncthreads();
-        for (int i = j; i < kLstmRows * kLstmH; i += kLstmThreads) hs[i / kLstmH][i % kLstmH] = ps[i / kLstmH][i % kLstmH];
+        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
+            const int r = i / kLstmH, u = i % kLstmH;
+            hs[u * kLstmRows + r] = ps[r * kG4 + u];
+        }
         __syncthreads();
     }
 }
 
 // BPTT. On entry gates holds post-activation i,f,g,o; on exit the pre-activation gradients dG.
-// dfeat [m, ldf]: its first 128 columns are dL/dh_{T-1}.
-__global__ void __launch_bounds__(kLstmThreads)
+// dfeat [m, ldf]: its first 128 columns are dL/dh_{T-1}. dh_{s-1} = dG_s W_hh is register-tiled like the forward
+// product: thread (q, kp) owns hidden units 2kp, 2kp+1 for all 8 rows over gate rows [128q, 128q+128); the four
+// partial sums are combined through shared memory. W_hh rows j < 256 (128 KB) stay in shared memory.
+constexpr int kLstmSmemJ = 256;
+constexpr size_t kLstmBwdSmem = ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 2 * kLstmRows * kLstmH + 4 * kLstmRows * kLstmH) * sizeof(float);
+
+__global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
                      const float* __restrict__ dfeat, int ldf, int m, int t) {
-    __shared__ float dh[kLstmRows][kLstmH];
-    __shared__ float dc[kLstmRows][kLstmH];
-    __shared__ float dgs[kLstmRows][kG4];
-    __shared__ float part[4][kLstmRows][kLstmH];
+    extern __shared__ __align__(16) float lstm_smem[];
+    float* Wh = lstm_smem;                          // [256][128]  W_hh rows j < 256
+    float* dgs = Wh + kLstmSmemJ * kLstmH;          // [512][8]    dG of this step, j-major
+    float* dh = dgs + kG4 * kLstmRows;              // [8][128]
+    float* dc = dh + kLstmRows * kLstmH;            // [8][128]
+    float* part = dc + kLstmRows * kLstmH;          // [4][8][128]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kLstmRows;
     const int nrows = min(kLstmRows, m - b0);
+    for (int i = tid; i < kLstmSmemJ * kLstmH / 4; i += kLstmThreads)
+        reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh) + i);
     for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
         const int r = i / kLstmH, u = i % kLstmH;
-        dh[r][u] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
-        dc[r][u] = 0.f;
+        dh[i] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
+        dc[i] = 0.f;
     }
     __syncthreads();
-    const int q = tid >> 7, k = tid & 127;  // 4 groups of 128 gate rows x 128 hidden units
+    const int q = tid >> 6, k0 = (tid & 63) * 2;
     for (int s = t - 1; s >= 0; s--) {
         for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
             const int r = i / kLstmH, u = i % kLstmH;
@@ -147,36 +182,49 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
                 const float ig = g[u], fg = g[kLstmH + u], gg = g[2 * kLstmH + u], og = g[3 * kLstmH + u];
                 const float tc = tanhf(cst[row * kLstmH + u]);
                 const float cp = s > 0 ? cst[(row - 1) * kLstmH + u] : 0.f;
-                const float dhv = dh[r][u];
-                const float dct = dc[r][u] + dhv * og * (1.f - tc * tc);
+                const float dhv = dh[i];
+                const float dct = dc[i] + dhv * og * (1.f - tc * tc);
                 d0 = dct * gg * ig * (1.f - ig);
                 d1 = dct * cp * fg * (1.f - fg);
                 d2 = dct * ig * (1.f - gg * gg);
                 d3 = dhv * tc * og * (1.f - og);
                 g[u] = d0; g[kLstmH + u] = d1; g[2 * kLstmH + u] = d2; g[3 * kLstmH + u] = d3;
-                dc[r][u] = dct * fg;
+                dc[i] = dct * fg;
             }
-            dgs[r][u] = d0; dgs[r][kLstmH + u] = d1; dgs[r][2 * kLstmH + u] = d2; dgs[r][3 * kLstmH + u] = d3;
+            dgs[u * kLstmRows + r] = d0;
+            dgs[(kLstmH + u) * kLstmRows + r] = d1;
+            dgs[(2 * kLstmH + u) * kLstmRows + r] = d2;
+            dgs[(3 * kLstmH + u) * kLstmRows + r] = d3;
         }
         __syncthreads();
         if (s > 0) {  // dh_{s-1}[r][k] = sum_j dG[r][j] W_hh[j][k]
-            float acc[kLstmRows];
+            float acc[kLstmRows][2];
 #pragma unroll
-            for (int r = 0; r < kLstmRows; r++) acc[r] = 0.f;
+            for (int r = 0; r < kLstmRows; r++) acc[r][0] = acc[r][1] = 0.f;
+            auto fma_j = [&](int j, float2 w) {
+                const float4 g0 = *reinterpret_cast<const float4*>(dgs + j * kLstmRows);
+                const float4 g1 = *reinterpret_cast<const float4*>(dgs + j * kLstmRows + 4);
+                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int r = 0; r < kLstmRows; r++) {
+                    acc[r][0] = fmaf(gv[r], w.x, acc[r][0]);
+                    acc[r][1] = fmaf(gv[r], w.y, acc[r][1]);
+                }
+            };
+            if (q * kLstmH < kLstmSmemJ) {  // warp-uniform: gate rows of this quarter are in shared memory
 #pragma unroll 8
-            for (int jj = 0; jj < kLstmH; jj++) {
-                const int jrow = q * kLstmH + jj;
-                const float w = __ldg(whh + (size_t)jrow * kLstmH + k);
-#pragma unroll
-                for (int r = 0; r < kLstmRows; r++) acc[r] = fmaf(dgs[r][jrow], w, acc[r]);
+                for (int jj = 0; jj < kLstmH; jj++) fma_j(q * kLstmH + jj, *reinterpret_cast<const float2*>(Wh + (q * kLstmH + jj) * kLstmH + k0));
+            } else {
+#pragma unroll 8
+                for (int jj = 0; jj < kLstmH; jj++)
+                    fma_j(q * kLstmH + jj, __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + jj) * kLstmH + k0)));
             }
 #pragma unroll
-            for (int r = 0; r < kLstmRows; r++) part[q][r][k] = acc[r];
+            for (int r = 0; r < kLstmRows; r++)
+                *reinterpret_cast<float2*>(part + (q * kLstmRows + r) * kLstmH + k0) = make_float2(acc[r][0], acc[r][1]);
             __syncthreads();
-            for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-                const int r = i / kLstmH, u = i % kLstmH;
-                dh[r][u] = (part[0][r][u] + part[1][r][u]) + (part[2][r][u] + part[3][r][u]);
-            }
+            for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads)
+                dh[i] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
             __syncthreads();
         }
     }
@@ -284,7 +332,12 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
     {
         // recurrent flops: 2 * 128 * 512 per (row, step)
         LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
-        lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, 0, st>>>(
+        static bool fwd_attr = false;
+        if (!fwd_attr) {
+            FI_CUDA_OK(cudaFuncSetAttribute(lstm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmFwdSmem));
+            fwd_attr = true;
+        }
+        lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
             w->gates, w->whh_t, params + T[3].offset, m, t, w->hprev, w->cst, w->feat);
         FI_TRY(ls.done());
     }
@@ -344,7 +397,12 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
     // d = dfeat [m, 612]; BPTT turns the stored gates into pre-activation gate gradients
     {
         LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
-        lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, 0, st>>>(w->gates, p->params + T[1].offset,
+        static bool bwd_attr = false;
+        if (!bwd_attr) {
+            FI_CUDA_OK(cudaFuncSetAttribute(lstm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmBwdSmem));
+            bwd_attr = true;
+        }
+        lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset,
                                                                                       w->cst, d, kFeat, m, t);
         FI_TRY(ls.done());
     }
