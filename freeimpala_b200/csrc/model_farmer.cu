@@ -67,8 +67,9 @@ __global__ void farmer_assemble_dense_kernel(const float* __restrict__ x, int m,
 // exit. Each CTA owns kLstmRows batch rows for all T steps (rows are independent: no inter-CTA synchronisation).
 // Per step the [8 x 128] x [128 x 512] product is register-tiled: thread t owns gate columns 2t, 2t+1 for all 8
 // rows (16 accumulators), reads h_{s-1} as two broadcast 16-byte shared-memory loads per k and the two weights as
-// one 8-byte load; the first 64 k-rows of W_hh^T (128 KB) stay in shared memory for the whole kernel, the other
-// half streams from L2. (The first version gave one column to each of 512 threads and re-read h with 1024
+// one 8-byte load; the whole of W_hh^T stays on chip for all T steps: k-rows 0..63 (128 KB) in shared memory,
+// k-rows 64..127 in registers (2 columns x 64 k = 128 registers per thread). The x-projection of the step is
+// loaded before the product and added after it, so its global-memory latency hides behind the FMAs. (The first version gave one column to each of 512 threads and re-read h with 1024
 // scalar broadcast loads per thread and step: shared-memory-issue bound at 10 us per step.)
 constexpr int kLstmSmemK = 64;  // k-rows of W_hh^T kept in shared memory
 constexpr size_t kLstmFwdSmem = ((size_t)kLstmSmemK * kG4 + kLstmRows * kG4 + kLstmH * kLstmRows + kLstmRows * kLstmH) * sizeof(float);
@@ -89,15 +90,20 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(whh_t) + i);
     for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) { hs[i] = 0.f; cs[i] = 0.f; }
     const float2 bias = __ldg(reinterpret_cast<const float2*>(b_hh + j0));
+    float2 wreg[kLstmH - kLstmSmemK];
+#pragma unroll
+    for (int k = 0; k < kLstmH - kLstmSmemK; k++)
+        wreg[k] = __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)(kLstmSmemK + k) * kG4 + j0));
     __syncthreads();
     for (int s = 0; s < t; s++) {
         float acc[kLstmRows][2];
+        float2 gx[kLstmRows];
 #pragma unroll
         for (int r = 0; r < kLstmRows; r++) {
-            float2 g = make_float2(0.f, 0.f);
-            if (r < nrows) g = *reinterpret_cast<const float2*>(gates + ((size_t)(b0 + r) * t + s) * kG4 + j0);
-            acc[r][0] = g.x + bias.x;
-            acc[r][1] = g.y + bias.y;
+            gx[r] = make_float2(0.f, 0.f);
+            if (r < nrows) gx[r] = *reinterpret_cast<const float2*>(gates + ((size_t)(b0 + r) * t + s) * kG4 + j0);
+            acc[r][0] = bias.x;
+            acc[r][1] = bias.y;
         }
         auto fma_k = [&](int k, float2 w) {
             const float4 h0 = *reinterpret_cast<const float4*>(hs + k * kLstmRows);
@@ -111,8 +117,13 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         };
 #pragma unroll 8
         for (int k = 0; k < kLstmSmemK; k++) fma_k(k, *reinterpret_cast<const float2*>(Ws + k * kG4 + j0));
-#pragma unroll 8
-        for (int k = kLstmSmemK; k < kLstmH; k++) fma_k(k, __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)k * kG4 + j0)));
+#pragma unroll
+        for (int k = kLstmSmemK; k < kLstmH; k++) fma_k(k, wreg[k - kLstmSmemK]);
+#pragma unroll
+        for (int r = 0; r < kLstmRows; r++) {
+            acc[r][0] += gx[r].x;
+            acc[r][1] += gx[r].y;
+        }
 #pragma unroll
         for (int r = 0; r < kLstmRows; r++) *reinterpret_cast<float2*>(ps + r * kG4 + j0) = make_float2(acc[r][0], acc[r][1]);
         __syncthreads();
@@ -147,7 +158,8 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
 // BPTT. On entry gates holds post-activation i,f,g,o; on exit the pre-activation gradients dG.
 // dfeat [m, ldf]: its first 128 columns are dL/dh_{T-1}. dh_{s-1} = dG_s W_hh is register-tiled like the forward
 // product: thread (q, kp) owns hidden units 2kp, 2kp+1 for all 8 rows over gate rows [128q, 128q+128); the four
-// partial sums are combined through shared memory. W_hh rows j < 256 (128 KB) stay in shared memory.
+// partial sums are combined through shared memory. W_hh stays on chip: the first 64 gate rows of every quarter
+// (128 KB) in shared memory, the other 64 in registers (128 per thread).
 constexpr int kLstmSmemJ = 256;
 constexpr size_t kLstmBwdSmem = ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 2 * kLstmRows * kLstmH + 4 * kLstmRows * kLstmH) * sizeof(float);
 
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
                      const float* __restrict__ dfeat, int ldf, int m, int t) {
     extern __shared__ __align__(16) float lstm_smem[];
-    float* Wh = lstm_smem;                          // [256][128]  W_hh rows j < 256
+    float* Wh = lstm_smem;                          // [4][64][128] W_hh rows 128q + jj, jj < 64
     float* dgs = Wh + kLstmSmemJ * kLstmH;          // [512][8]    dG of this step, j-major
     float* dh = dgs + kG4 * kLstmRows;              // [8][128]
     float* dc = dh + kLstmRows * kLstmH;            // [8][128]
@@ -163,15 +175,21 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kLstmRows;
     const int nrows = min(kLstmRows, m - b0);
-    for (int i = tid; i < kLstmSmemJ * kLstmH / 4; i += kLstmThreads)
-        reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh) + i);
+    for (int i = tid; i < kLstmSmemJ * kLstmH / 4; i += kLstmThreads) {
+        const int row = i / (kLstmH / 4), c4 = i % (kLstmH / 4);       // smem row = 64 * quarter + jj
+        const int j = (row >> 6) * kLstmH + (row & 63);
+        reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * kLstmH) + c4);
+    }
     for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
         const int r = i / kLstmH, u = i % kLstmH;
         dh[i] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
         dc[i] = 0.f;
     }
-    __syncthreads();
     const int q = tid >> 6, k0 = (tid & 63) * 2;
+    float2 wreg[64];
+#pragma unroll
+    for (int jj = 0; jj < 64; jj++) wreg[jj] = __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + 64 + jj) * kLstmH + k0));
+    __syncthreads();
     for (int s = t - 1; s >= 0; s--) {
         for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
             const int r = i / kLstmH, u = i % kLstmH;
@@ -211,14 +229,10 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
                     acc[r][1] = fmaf(gv[r], w.y, acc[r][1]);
                 }
             };
-            if (q * kLstmH < kLstmSmemJ) {  // warp-uniform: gate rows of this quarter are in shared memory
 #pragma unroll 8
-                for (int jj = 0; jj < kLstmH; jj++) fma_j(q * kLstmH + jj, *reinterpret_cast<const float2*>(Wh + (q * kLstmH + jj) * kLstmH + k0));
-            } else {
-#pragma unroll 8
-                for (int jj = 0; jj < kLstmH; jj++)
-                    fma_j(q * kLstmH + jj, __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + jj) * kLstmH + k0)));
-            }
+            for (int jj = 0; jj < 64; jj++) fma_j(q * kLstmH + jj, *reinterpret_cast<const float2*>(Wh + (q * 64 + jj) * kLstmH + k0));
+#pragma unroll
+            for (int jj = 0; jj < 64; jj++) fma_j(q * kLstmH + 64 + jj, wreg[jj]);
 #pragma unroll
             for (int r = 0; r < kLstmRows; r++)
                 *reinterpret_cast<float2*>(part + (q * kLstmRows + r) * kLstmH + k0) = make_float2(acc[r][0], acc[r][1]);
