@@ -16,16 +16,16 @@
 // K=512 (1.7e-6 of the largest sum). Halving the chunk only gave 5.0e-5: what is left is the truncation
 // inside each MMA's own 8-term sum, which no promotion schedule removes.
 //
-// Kernel anatomy (one CTA per SM, persistent over output tiles; 256 threads):
+// Kernel anatomy (one CTA per SM, persistent over output tiles; 128 control threads + 4 or 8 promotion warps):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A_hi, A_lo, B_hi, B_lo into a
 //              multi-stage shared-memory ring, completion on mbarriers;
 //   warp 1     MMA issuer: one elected lane issues 2 tcgen05.mma (M=128, K=8; N=2*BN and N=BN) x 4 k-slices per
 //              32-wide k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
 //   warp 2     TMEM allocator: 2 chunk buffers of [main | corr] = 2*BN fp32 columns each, so the promotion of
 //              chunk i overlaps the MMAs of chunk i+1 and the epilogue of tile j those of tile j+1;
-//   warps 4-7  promotion + epilogue: tcgen05.ld (32 lanes x 32 columns per warp) into BN register accumulators per
-//              thread, then bias / ReLU / ReLU-mask and either a plain fp32 store or the hi/lo split store that
-//              feeds the next GEMM.
+//   warps 4..  promotion + epilogue, two warps per TMEM lane quarter (each owns half of the tile's columns):
+//              tcgen05.ld (32 lanes x 32 columns) into register accumulators, then bias / ReLU / ReLU-mask and
+//              either a plain fp32 store or the hi/lo split store (TMA) that feeds the next GEMM.
 // Operand layouts (UMMA "major"): K-major tiles are [rows][32 k] with one 128-byte row per matrix row (128B
 // swizzle, 16-byte atoms); MN-major tiles are [32 k][32 mn] boxes (the reduction index is the slow one; tf32 only
 // supports the 128B swizzle with 32-byte atoms there), so dgrad (B = W[n,k] read along n) and wgrad (both operands
@@ -40,7 +40,7 @@ namespace fi {
 
 constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
-constexpr int kTcThreads = 256;
+constexpr int kTcCtrlThreads = 128;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, (idle)
 constexpr int kTcChunk = 4;      // k-blocks accumulated in TMEM before promotion to registers (16 wide MMAs)
 constexpr int kTcSmemLimit = 227 * 1024;
 
@@ -159,14 +159,20 @@ struct TcCfg {
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static constexpr int kStages = BN >= 128 ? 3 : 4;
     static constexpr int kTmemCols = 4 * BN;                          // 2 chunk buffers x [main | corr] (a power of two >= 32)
-    static constexpr int kOutTileBytes = 4 * 2 * 32 * 128;            // per epilogue warp: hi + lo staging tiles of 32 x 128 B
+    // promotion + epilogue warps: two per TMEM lane quarter (each owns half of the tile's columns) once the tile is
+    // wide enough, so that every SM sub-partition has two warps to interleave (one warp per scheduler issued at
+    // ~0.25 instructions per clock and made the promotion side, not the MMAs, the critical path).
+    static constexpr int kPromoWarps = BN >= 64 ? 8 : 4;
+    static constexpr int kColsPerWarp = BN / (kPromoWarps / 4);
+    static constexpr int kThreads = kTcCtrlThreads + 32 * kPromoWarps;
+    static constexpr int kOutTileBytes = kPromoWarps * 32 * 128;      // per promotion warp: one 32 x 128 B staging tile
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
 };
 
 // One kernel for the three operand-major combinations. A_MN / B_MN: operand is MN-major (reduction index slow).
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(TcCfg<BN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
@@ -198,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(main_full_bar(s), 1);
-            mbar_init(main_empty_bar(s), 4);  // one arrival per promotion warp
+            mbar_init(main_empty_bar(s), Cfg::kPromoWarps);  // one arrival per promotion warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -306,7 +312,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===================== promotion + epilogue =====================
-        const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+        constexpr int CW = Cfg::kColsPerWarp;     // columns of the tile owned by this warp
+        const int pw = warp - 4;
+        const int q = pw & 3;                     // TMEM lane quarter this warp may access (warp id % 4)
+        const int nc0 = (pw >> 2) * CW;           // first tile column of this warp
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int mb = 0;
         uint32_t mphase = 0;
@@ -316,27 +325,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < sh.m;
-            float acc[BN];
+            float acc[CW];
 #pragma unroll
-            for (int i = 0; i < BN; i++) acc[i] = 0.f;
+            for (int i = 0; i < CW; i++) acc[i] = 0.f;
             // bit-packed ReLU mask of this thread's row: one 16-byte load per tile, issued before the k-loop so that
             // its latency hides behind the MMAs (a float mask read in the epilogue was latency-bound: 4 warps per SM)
-            uint32_t mw[BN / 32];
+            uint32_t mw[CW / 32];
 #pragma unroll
-            for (int c = 0; c < BN / 32; c++) mw[c] = 0xFFFFFFFFu;
+            for (int c = 0; c < CW / 32; c++) mw[c] = 0xFFFFFFFFu;
             if (ep.mask_bits && row_ok) {
 #pragma unroll
-                for (int c = 0; c < BN / 32; c++)
-                    if (n0 + c * 32 < sh.n) mw[c] = __ldg(ep.mask_bits + (size_t)row * ep.mask_ldw + (n0 >> 5) + c);
+                for (int c = 0; c < CW / 32; c++)
+                    if (n0 + nc0 + c * 32 < sh.n) mw[c] = __ldg(ep.mask_bits + (size_t)row * ep.mask_ldw + ((n0 + nc0) >> 5) + c);
             }
             for (int kc = kb0; kc < kb1; kc += kTcChunk) {
                 mbar_wait(main_full_bar(mb), mphase);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = 0; c < CW / 32; c++) {
                     uint32_t v[32], u[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + c * 32), v);       // main
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + c * 32), u);  // corr
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + nc0 + c * 32), v);       // main
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + nc0 + c * 32), u);  // corr
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i++)  // round-to-nearest promotion
@@ -352,10 +361,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // c[col * ldc + row]: lanes hold consecutive rows, so the register layout is already coalesced
                 if (row_ok && cplain) {
 #pragma unroll
-                    for (int c = 0; c < BN / 32; c++) {
+                    for (int c = 0; c < CW / 32; c++) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
-                            const int col = n0 + c * 32 + i;
+                            const int col = n0 + nc0 + c * 32 + i;
                             if (col < sh.n) cplain[(size_t)col * ep.ldc + row] = acc[c * 32 + i];
                         }
                     }
@@ -364,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             if (ep.mask_bits) {
 #pragma unroll
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = 0; c < CW / 32; c++) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) acc[c * 32 + i] = ((mw[c] >> i) & 1u) ? acc[c * 32 + i] : 0.f;
                 }
@@ -375,35 +384,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // one lane hands both tiles to the TMA (cp.async.bulk.tensor store): no per-element address arithmetic
                 // and no store instructions on the critical path of the 4 promotion warps. Rows / columns beyond the
                 // matrix are clipped by the TMA.
-                const uint32_t out_hi = out_tiles + (uint32_t)q * 8192u, out_lo = out_hi + 4096u;
+                const uint32_t stage_tile = out_tiles + (uint32_t)pw * 4096u;  // one 32 x 128 B tile, reused for hi then lo
                 const int rbase = m0 + q * 32;
 #pragma unroll
-                for (int c = 0; c < BN / 32; c++) {
-                    const int col0 = n0 + c * 32;
+                for (int c = 0; c < CW / 32; c++) {
+                    const int col0 = n0 + nc0 + c * 32;
                     if (col0 >= sh.n) continue;  // warp-uniform
-                    if (lane == 0) tma_store_wait_read();  // the previous block's stores have left the staging tiles
-                    __syncwarp();
+                    float x[32];
                     uint32_t bits = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float t[4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int i = 4 * j + e;
-                            float x = acc[c * 32 + i];
-                            if (ep.bias && col0 + i < sh.n) x += __ldg(ep.bias + col0 + i);
-                            if (ep.relu) x = fmaxf(x, 0.f);
-                            bits |= (x > 0.f ? 1u : 0u) << i;
-                            t[e] = x;
-                        }
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(t[0]) & 0xFFFFE000u); l.x = t[0] - h.x;
-                        h.y = __uint_as_float(__float_as_uint(t[1]) & 0xFFFFE000u); l.y = t[1] - h.y;
-                        h.z = __uint_as_float(__float_as_uint(t[2]) & 0xFFFFE000u); l.z = t[2] - h.z;
-                        h.w = __uint_as_float(__float_as_uint(t[3]) & 0xFFFFE000u); l.w = t[3] - h.w;
-                        const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);  // 128B swizzle
-                        st_shared_v4(out_hi + off, h);
-                        st_shared_v4(out_lo + off, l);
+                    for (int i = 0; i < 32; i++) {
+                        float t = acc[c * 32 + i];
+                        if (ep.bias && col0 + i < sh.n) t += __ldg(ep.bias + col0 + i);
+                        if (ep.relu) t = fmaxf(t, 0.f);
+                        bits |= (t > 0.f ? 1u : 0u) << i;
+                        x[i] = t;
                     }
                     if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
                     if (ep.colsum_out) {
@@ -413,10 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         float y16[16], y8[8], y4[4], y2[2];
                         const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float lo_v = acc[c * 32 + i], hi_v = acc[c * 32 + 16 + i];
-                            y16[i] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xFFFFFFFFu, b16 ? lo_v : hi_v, 16);
-                        }
+                        for (int i = 0; i < 16; i++) y16[i] = (b16 ? x[16 + i] : x[i]) + __shfl_xor_sync(0xFFFFFFFFu, b16 ? x[i] : x[16 + i], 16);
 #pragma unroll
                         for (int i = 0; i < 8; i++) y8[i] = (b8 ? y16[8 + i] : y16[i]) + __shfl_xor_sync(0xFFFFFFFFu, b8 ? y16[i] : y16[8 + i], 8);
 #pragma unroll
@@ -424,15 +416,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 2; i++) y2[i] = (b2 ? y4[2 + i] : y4[i]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? y4[i] : y4[2 + i], 2);
                         const float y1 = (b1 ? y2[1] : y2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? y2[0] : y2[1], 1);
-                        if (col0 + lane < sh.n)
-                            ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
+                        if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&map_c_hi, out_hi, col0, rbase);
-                        tma_store_2d(&map_c_lo, out_lo, col0, rbase);
-                        tma_store_commit();
+                    // hi tile, then lo tile, through the same staging buffer: the sibling warp on this scheduler runs while
+                    // lane 0 waits for the previous bulk store to have read the buffer
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 o;
+                            const float h0 = __uint_as_float(__float_as_uint(x[4 * j + 0]) & 0xFFFFE000u);
+                            const float h1 = __uint_as_float(__float_as_uint(x[4 * j + 1]) & 0xFFFFE000u);
+                            const float h2 = __uint_as_float(__float_as_uint(x[4 * j + 2]) & 0xFFFFE000u);
+                            const float h3 = __uint_as_float(__float_as_uint(x[4 * j + 3]) & 0xFFFFE000u);
+                            if (part == 0) o = make_float4(h0, h1, h2, h3);
+                            else o = make_float4(x[4 * j + 0] - h0, x[4 * j + 1] - h1, x[4 * j + 2] - h2, x[4 * j + 3] - h3);
+                            st_shared_v4(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), o);  // 128B swizzle
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(part == 0 ? &map_c_hi : &map_c_lo, stage_tile, col0, rbase);
+                            tma_store_commit();
+                        }
                     }
                 }
                 continue;
@@ -441,16 +449,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // instruction touch 32 different rows. Transpose each 32x32 block through this warp's padded shared-memory
             // tile so that a store instruction writes 128 contiguous bytes of one row; bias, ReLU and the hi/lo split are
             // applied after the transpose, where lane = column.
-            float* stg = reinterpret_cast<float*>(smem_raw + (out_tiles - smem_u32(smem_raw)) + q * 8192);  // [32][33] floats
+            float* stg = reinterpret_cast<float*>(smem_raw + (out_tiles - smem_u32(smem_raw)) + pw * 4096);  // [32][32], XOR-swizzled
             const int rbase = m0 + q * 32;
             const int rows_here = min(32, sh.m - rbase);
 #pragma unroll
-            for (int c = 0; c < BN / 32; c++) {
-                const int col0 = n0 + c * 32;
+            for (int c = 0; c < CW / 32; c++) {
+                const int col0 = n0 + nc0 + c * 32;
                 if (col0 >= sh.n || rows_here <= 0) continue;  // warp-uniform
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; i++) stg[lane * 33 + i] = acc[c * 32 + i];
+                for (int i = 0; i < 32; i++) stg[lane * 32 + (i ^ lane)] = acc[c * 32 + i];
                 __syncwarp();
                 const int col = col0 + lane;
                 const bool col_ok = col < sh.n;
@@ -465,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     float tv[8], mv[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        tv[u] = stg[(rr0 + u) * 33 + lane];
+                        tv[u] = stg[(rr0 + u) * 32 + (lane ^ (rr0 + u))];
                         mv[u] = 1.f;
                         if (pm && col_ok && rr0 + u < rows_here) mv[u] = __ldg(pm + (size_t)u * ep.ldmask);
                     }
@@ -599,7 +607,7 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
     const char* label = !B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>");
     LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
     return ls.done();
 }
 
