@@ -320,7 +320,7 @@ int fi_ring_read_batch(fi_ring* r, size_t batch_size, void* stream, fi_batch* ou
         FI_CUDA_OK(cudaMalloc((void**)&r->dev_batch, batch_size * r->slot_bytes));
         r->batch_cap = batch_size;
     }
-    const size_t first = r->read_index, last = (first + batch_size - 1) % r->capacity;
+    const size_t first = r->read_index;
     // every published slot goes to HBM now; copies are issued in FIFO order on one stream, so the tail event covers all
     ring_flush_locked(r, true);
     FI_CUDA_OK(cudaStreamWaitEvent(st, r->h2d_tail, 0));
