@@ -295,20 +295,35 @@ def run_b200_arm(args):
     e2e = None
     if not args.no_e2e:
         ring = L.getSharedBuffers()[0]
-        nw = args.writers if args.writers > 0 else max(2, min(16, (os.cpu_count() or 8) // world))
+        cores_per_rank = max(1, (os.cpu_count() or 8) // world)
+        nw_copy = args.writers if args.writers > 0 else max(2, min(16, cores_per_rank))
+        nw_zc = 2  # in-place producers only take the ring lock: two threads keep the ring full
 
-        per = (M + nw - 1) // nw
-
-        def writer(j: int, steps: int):
-            # actor thread j owns trajectories [j*per, (j+1)*per) of every step and hands them over in bursts of 16
+        def copy_writer(j: int, steps: int, nw: int):
+            # actor thread j owns trajectories [j*per, (j+1)*per) of every step: SharedBuffer::write semantics (the ring
+            # copies the caller's bytes into the pinned slot), handed over in bursts of 16
+            per = (M + nw - 1) // nw
             for s in range(steps):
                 base = (s % 2) * M
                 lo, hi = j * per, min(M, (j + 1) * per)
                 for i in range(lo, hi, 16):
                     ring.write_many(host[base + i:base + min(i + 16, hi)])
 
-        def e2e_steps(steps: int):
-            ts = [threading.Thread(target=writer, args=(j, steps)) for j in range(nw)]
+        def inplace_writer(j: int, steps: int, nw: int):
+            # zero-copy producer (fi_ring_reserve_many / fi_ring_commit_many): the trajectory is produced IN the pinned slot
+            # (what an MPI_Irecv posted into the slot does); here the slot keeps the synthetic trajectory written during
+            # warm-up and the producer stamps the step number into an unused word of its first record
+            burst = 32
+            for s in range(steps):
+                for i in range(j * burst, M, nw * burst):
+                    n = min(burst, M - i)
+                    ptrs, ticket = ring.reserve_many(n)
+                    for ptr in ptrs:
+                        C.c_uint32.from_address(ptr + 4 * 255).value = s
+                    ring.commit_many(ticket, n)
+
+        def e2e_steps(steps: int, writer, nw: int):
+            ts = [threading.Thread(target=writer, args=(j, steps, nw)) for j in range(nw)]
             for t in ts:
                 t.start()
             for _ in range(steps):
@@ -318,23 +333,32 @@ def run_b200_arm(args):
             for t in ts:
                 t.join()
 
-        e2e_steps(max(W, 3))
-        L.sync(0)
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_steps(K)
-        L.sync(0)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        barrier()
-        windows.append((t0, t1))
-        e2e_s = max_over_ranks(t1 - t0)
-        e2e = {"value": world * M * T * K / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / K * 1e3,
+        def timed(writer, nw):
+            L.sync(0)
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_steps(K, writer, nw)
+            L.sync(0)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            barrier()
+            windows.append((t0, t1))
+            return max_over_ranks(t1 - t0)
+
+        e2e_steps(max(W, 4), copy_writer, nw_copy)   # warm-up; also leaves a valid trajectory in each of the 2M pinned slots
+        zc_s = timed(inplace_writer, nw_zc)
+        copy_s = timed(copy_writer, nw_copy)
+        e2e = {"value": world * M * T * K / zc_s, "unit": UNIT, "ms_per_step": zc_s / K * 1e3,
                "h2d_bytes_per_step": world * M * slot_bytes,
                "d2h_bytes_per_step": world * (32 + 4 * L.param_count),
-               "path": f"fi_ring_write x{M} per step from {nw} actor threads in bursts of 16 (pinned slot + cudaMemcpyAsync on the side "
-                       f"stream) -> readBatch (gather kernel) -> Learner.trainModel -> losses D2H; weights published D2H"}
+               "path": f"trajectories produced in place in the ring's pinned slots (fi_ring_reserve_many / fi_ring_commit_many, "
+                       f"{nw_zc} producer threads) -> cudaMemcpyAsync per run of slots on the side stream -> readBatch (gather "
+                       f"kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H every step",
+               "write_copy": {"value": world * M * T * K / copy_s, "ms_per_step": copy_s / K * 1e3, "actor_threads": nw_copy,
+                              "host_cores_per_rank": cores_per_rank,
+                              "path": "same, but through SharedBuffer::write semantics (fi_ring_write_many): every trajectory is "
+                                      "first copied from the actor's buffer into the pinned slot by the host"}}
 
     clocks = sampler.stop(windows) if rank == 0 else None
 

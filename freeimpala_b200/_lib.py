@@ -56,6 +56,8 @@ SIGNATURES = {
     "fi_ring_write_many": (c_size_t, [_P, _P, c_size_t, c_size_t, c_size_t]),
     "fi_ring_reserve": (_P, [_P, C.POINTER(c_u64)]),
     "fi_ring_commit": (c_int, [_P, c_u64, c_size_t]),
+    "fi_ring_reserve_many": (c_size_t, [_P, c_size_t, _P, C.POINTER(c_u64)]),
+    "fi_ring_commit_many": (c_int, [_P, c_u64, c_size_t, c_size_t]),
     "fi_ring_read_batch": (c_int, [_P, c_size_t, _P, C.POINTER(FiBatch)]),
     "fi_ring_set_draining": (None, [_P]),
     "fi_ring_filled_count": (c_size_t, [_P]),

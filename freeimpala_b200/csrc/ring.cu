@@ -298,6 +298,45 @@ int fi_ring_commit(fi_ring* r, uint64_t ticket, size_t n) {
     return ring_commit(r, (size_t)(ticket % r->capacity), n);
 }
 
+size_t fi_ring_reserve_many(fi_ring* r, size_t count, void** slots, uint64_t* first_ticket) {
+    if (!r || count == 0 || count > r->capacity) return 0;
+    size_t first;
+    {
+        std::unique_lock<std::mutex> lock(r->mu);
+        r->not_full.wait(lock, [&] { return r->count + r->reserved + count <= r->capacity; });
+        first = r->write_index;
+        r->write_index = (first + count) % r->capacity;
+        r->reserved += count;
+        if (first_ticket) *first_ticket = r->ticket_next;
+        r->ticket_next += count;
+    }
+    cudaSetDevice(r->device);
+    for (size_t i = 0; i < count; i++) {
+        const size_t slot = (first + i) % r->capacity;
+        ring_wait_slot_copied(r, slot);  // the previous occupant has reached HBM
+        if (slots) slots[i] = r->host_slots + slot * r->slot_bytes;
+    }
+    return count;
+}
+
+int fi_ring_commit_many(fi_ring* r, uint64_t first_ticket, size_t count, size_t n) {
+    if (!r || n > r->slot_bytes || count == 0 || count > r->capacity) return 0;
+    int published;
+    {
+        std::lock_guard<std::mutex> lock(r->mu);
+        for (size_t i = 0; i < count; i++) {
+            const size_t slot = (size_t)((first_ticket + i) % r->capacity);
+            r->committed[slot] = 1;
+            r->commit_bytes[slot] = n;
+        }
+        cudaSetDevice(r->device);
+        published = ring_publish_locked(r);
+    }
+    if (published == 1) r->not_empty.notify_one();
+    else if (published > 1) r->not_empty.notify_all();
+    return 1;
+}
+
 int fi_ring_read_batch(fi_ring* r, size_t batch_size, void* stream, fi_batch* out) {
     if (!r || !out) return set_error(FI_ERR_ARG, "fi_ring_read_batch: null argument");
     memset(out, 0, sizeof(*out));

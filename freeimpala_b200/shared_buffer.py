@@ -111,6 +111,17 @@ class SharedBuffer:
         view = np.ctypeslib.as_array((C.c_uint8 * self.slot_bytes).from_address(p))
         return view, ticket.value
 
+    def reserve_many(self, count: int):
+        """Reserve `count` consecutive pinned slots: (list of slot addresses, first ticket)."""
+        ticket = C.c_uint64()
+        ptrs = (C.c_void_p * count)()
+        if self._lib.fi_ring_reserve_many(self._h, count, ptrs, C.byref(ticket)) != count:
+            raise _lib.FiError(_lib.FI_ERR_ARG, "fi_ring_reserve_many", "count must be in [1, capacity]")
+        return list(ptrs), ticket.value
+
+    def commit_many(self, first_ticket: int, count: int, n: int | None = None) -> bool:
+        return bool(self._lib.fi_ring_commit_many(self._h, first_ticket, count, self.slot_bytes if n is None else n))
+
     def commit(self, ticket: int, n: int | None = None) -> bool:
         return bool(self._lib.fi_ring_commit(self._h, ticket, self.slot_bytes if n is None else n))
 

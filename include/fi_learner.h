@@ -103,6 +103,13 @@ FI_API size_t fi_ring_write_many(fi_ring* ring, const void* src, size_t count, s
 FI_API void* fi_ring_reserve(fi_ring* ring, uint64_t* ticket);
 FI_API int fi_ring_commit(fi_ring* ring, uint64_t ticket, size_t n);
 
+/* Burst form of the zero-copy producer: reserve `count` consecutive slots at once (blocks until that many are
+ * free; count <= capacity), e.g. to post `count` MPI_Irecv's straight into pinned memory (slots[i] receives the
+ * address of the i-th slot; may be NULL when the caller tracks addresses itself), then commit them together.
+ * Returns count / 1 on success, 0 on a bad argument. */
+FI_API size_t fi_ring_reserve_many(fi_ring* ring, size_t count, void** slots, uint64_t* first_ticket);
+FI_API int fi_ring_commit_many(fi_ring* ring, uint64_t first_ticket, size_t count, size_t n);
+
 /* SharedBuffer::readBatch (data_structures.h:267-300). Blocks until count >= M or draining.
  * Draining with count < M: out->num_slots = 0 and returns 0 (the caller breaks/continues,
  * learner.h:79-84). Otherwise consumes exactly M slots FIFO with wraparound, wakes all

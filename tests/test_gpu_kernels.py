@@ -170,6 +170,29 @@ def test_ring_zero_copy_reserve_commit(fi, torch_cuda):
     ring.close()
 
 
+def test_ring_reserve_many_commit_many(fi, torch_cuda):
+    import ctypes as C
+    ring = fi.SharedBuffer(1, 8)
+    ptrs, ticket = ring.reserve_many(5)
+    assert len(ptrs) == 5 and ring.getFilledCount() == 0
+    for i, p in enumerate(ptrs):
+        C.memset(p, i + 1, 1024)
+    assert ring.commit_many(ticket, 5)
+    assert ring.getFilledCount() == 5
+    out = ring.readBatch(5).to_host()
+    assert all(np.all(out[i] == i + 1) for i in range(5))
+    ptrs, ticket = ring.reserve_many(6)            # wraps around the ring end (slots 5,6,7,0,1,2)
+    for i, p in enumerate(ptrs):
+        C.memset(p, 10 + i, 1024)
+    ring.commit_many(ticket, 6, 100)               # short commit: bytes [100, 1024) keep the previous occupant
+    out = ring.readBatch(6).to_host()
+    assert all(np.all(out[i, :100] == 10 + i) for i in range(6))
+    assert np.all(out[3, 100:] == 1) and np.all(out[0, 100:] == 10)   # slot 0 held the first batch; slot 5 was only memset
+    with pytest.raises(fi.FiError):
+        ring.reserve_many(9)                       # more than the capacity can never be reserved
+    ring.close()
+
+
 # ------------------------------------------------------------------------------- Adam
 @pytest.mark.parametrize("kind,n", [("adam", 1514497), ("adamw", 10007), ("sgd", 4099), ("adam", 3), ("adam", 1142801)])
 def test_fused_optimizer_bit_exact_vs_f32_oracle(fi, oracle, torch_cuda, kind, n):
