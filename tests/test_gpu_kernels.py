@@ -187,7 +187,8 @@ def test_ring_reserve_many_commit_many(fi, torch_cuda):
     ring.commit_many(ticket, 6, 100)               # short commit: bytes [100, 1024) keep the previous occupant
     out = ring.readBatch(6).to_host()
     assert all(np.all(out[i, :100] == 10 + i) for i in range(6))
-    assert np.all(out[3, 100:] == 1) and np.all(out[0, 100:] == 10)   # slot 0 held the first batch; slot 5 was only memset
+    # only the committed bytes travel: the tail is the slot's previous content in HBM (first batch / zero-initialised)
+    assert np.all(out[3, 100:] == 1) and np.all(out[0, 100:] == 0)
     with pytest.raises(fi.FiError):
         ring.reserve_many(9)                       # more than the capacity can never be reserved
     ring.close()
