@@ -24,7 +24,7 @@ def _ac_learner(fi, m, t, **kw):
 
 
 @pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
-@pytest.mark.parametrize("m,t,steps", [(4, 7, 3), (64, 100, 3), (9, 33, 2)])
+@pytest.mark.parametrize("m,t,steps", [(4, 7, 3), (64, 100, 3), (9, 33, 2), (2, 1, 2), (1, 130, 1)])
 def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
     params = U.ac_params(11)
     L = _ac_learner(fi, m, t, gemm_mode=gemm_mode, entropy_cost=0.01, baseline_cost=0.5)
@@ -56,6 +56,25 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
         parity.step(grads)
         parity.check(L.get_params(0), TOL)
     assert L.steps_done(0) == steps
+    L.close()
+
+
+@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+def test_partial_batch_smaller_than_configured(fi, oracle, gemm_mode):
+    """A batch of fewer trajectories than batch_size (the learner's buffers are sized for M) is a valid step."""
+    m_cfg, m, t = 6, 3, 5
+    params = U.ac_params(8)
+    L = _ac_learner(fi, m_cfg, t, gemm_mode=gemm_mode)
+    L.set_params(0, params)
+    obs, mu, act, rew, disc, boot = U.vtrace_batch(31, m, t)
+    O = oracle.actor_critic(params, lr=5e-4)
+    L.forward_backward(0, L.stage_batch(0, po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)))
+    want, n_over, max_over = O.loss_grad_masked(obs, mu, act, rew, disc, boot, L.debug_relu_masks(0, m * t))
+    assert n_over <= 4 and max_over < 1e-5
+    np.testing.assert_allclose(L.last_losses(0), want, rtol=TOL, atol=1e-6 * abs(want[0]))
+    assert U.rel_l2(L.get_grads(0), O.grads()) < TOL
+    with pytest.raises(fi.FiError):
+        L.stage_batch(0, np.zeros((m_cfg + 1, t * 1024), np.uint8))      # more than batch_size is rejected
     L.close()
 
 
