@@ -32,6 +32,7 @@
 // read along the batch rows) need no transposed copies.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "fi_internal.cuh"
@@ -109,6 +110,46 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier
+// (peer bit of the barrier address cleared, as cute::SM100_TMA_2SM_LOAD_2D does)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -153,11 +194,16 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one SM pair) work on one 256 x BN tile with cta_group::2 MMAs. Each CTA holds its own
+// 128 rows of A and HALF of the B tile (BN/2 rows), the tensor core reads the other half from the peer: the B operand
+// traffic through each SM's shared memory halves (the 1-CTA kernel is shared-memory-bandwidth bound).
+template <int BN, bool PAIR = false>
 struct TcCfg {
-    static constexpr int kStageBytes = 2 * (kTcBM + BN) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;                 // rows of the B tile held by one CTA
+    static constexpr int kStageBytes = 2 * (kTcBM + kBRows) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
-    static constexpr int kStages = BN >= 128 ? 3 : 4;
+    static_assert(!PAIR || BN == 128, "pair mode is built for BN = 128");
+    static constexpr int kStages = PAIR ? 4 : (BN >= 128 ? 3 : 4);
     static constexpr int kTmemCols = 4 * BN;                          // 2 chunk buffers x [main | corr] (a power of two >= 32)
     // promotion + epilogue warps: two per TMEM lane quarter (each owns half of the tile's columns) once the tile is
     // wide enough, so that every SM sub-partition has two warps to interleave (one warp per scheduler issued at
@@ -171,16 +217,20 @@ struct TcCfg {
 };
 
 // One kernel for the three operand-major combinations. A_MN / B_MN: operand is MN-major (reduction index slow).
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TcCfg<BN>::kThreads, 1)
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
+__global__ void __launch_bounds__(TcCfg<BN, PAIR>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
                const TcShape sh, const TcEpilogue ep) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, PAIR>;
     constexpr int kStages = Cfg::kStages;
     constexpr uint32_t kABytes = kTcBM * kTcBK * 4;   // one of A_hi / A_lo
-    constexpr uint32_t kBBytes = BN * kTcBK * 4;
+    constexpr uint32_t kBBytes = Cfg::kBRows * kTcBK * 4;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // CTA (or CTA pair) index
+    const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int kTileM = PAIR ? 2 * kTcBM : kTcBM;
     constexpr uint32_t kBoxBytes = 32 * kTcBK * 4;    // one MN-major box: 32 k-rows x 128 B
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
@@ -204,17 +254,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(main_full_bar(s), 1);
-            mbar_init(main_empty_bar(s), Cfg::kPromoWarps);  // one arrival per promotion warp
+            // one arrival per promotion warp; in pair mode the leader's barrier also collects the peer's warps
+            mbar_init(main_empty_bar(s), (PAIR ? 2 : 1) * Cfg::kPromoWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -225,35 +283,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+                if constexpr (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1);
+                else tma_load_2d(dst, map, bar, c0, c1);
+            };
+            for (int w = unit; w < total_work; w += num_units) {
                 const int tile = w % tiles, split = w / tiles;
-                const int m0 = (tile / sh.num_n_blocks) * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
+                // this CTA's rows of A and rows of the B tile (pair mode: the second CTA takes the second half of each)
+                const int m0 = (tile / sh.num_n_blocks) * kTileM + (int)cta_rank * kTcBM;
+                const int n0 = (tile % sh.num_n_blocks) * BN + (int)cta_rank * Cfg::kBRows * (PAIR ? 1 : 0);
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t bar = full_bar(stage);
-                    mbar_expect_tx(bar, Cfg::kStageBytes);
+                    // pair mode: both CTAs' loads are credited to the leader's barrier, which expects both stages
+                    if (!PAIR || cta_rank == 0) mbar_expect_tx(bar, (PAIR ? 2 : 1) * Cfg::kStageBytes);
                     const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
                     const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
                     const int k0 = kb * kTcBK;
                     if constexpr (!A_MN) {
-                        tma_load_2d(a_hi, &map_a_hi, bar, k0, m0);
-                        tma_load_2d(a_lo, &map_a_lo, bar, k0, m0);
+                        load(a_hi, &map_a_hi, bar, k0, m0);
+                        load(a_lo, &map_a_lo, bar, k0, m0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < kTcBM / 32; j++) {
-                            tma_load_2d(a_hi + j * kBoxBytes, &map_a_hi, bar, m0 + j * 32, k0);
-                            tma_load_2d(a_lo + j * kBoxBytes, &map_a_lo, bar, m0 + j * 32, k0);
+                            load(a_hi + j * kBoxBytes, &map_a_hi, bar, m0 + j * 32, k0);
+                            load(a_lo + j * kBoxBytes, &map_a_lo, bar, m0 + j * 32, k0);
                         }
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(b_hi, &map_b_hi, bar, k0, n0);
-                        tma_load_2d(b_lo, &map_b_lo, bar, k0, n0);
+                        load(b_hi, &map_b_hi, bar, k0, n0);
+                        load(b_lo, &map_b_lo, bar, k0, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; j++) {
-                            tma_load_2d(b_hi + j * kBoxBytes, &map_b_hi, bar, n0 + j * 32, k0);
-                            tma_load_2d(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * 32, k0);
+                        for (int j = 0; j < Cfg::kBRows / 32; j++) {
+                            load(b_hi + j * kBoxBytes, &map_b_hi, bar, n0 + j * 32, k0);
+                            load(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * 32, k0);
                         }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -262,9 +327,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc_wide = umma_idesc(kTcBM, 2 * BN, A_MN ? 1 : 0, B_MN ? 1 : 0);  // A_hi [B_hi | B_lo]
-            constexpr uint32_t idesc_half = umma_idesc(kTcBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);       // A_lo B_hi
+            constexpr uint32_t idesc_half = umma_idesc(kTileM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);      // A_lo B_hi (pair: every product)
             // K-major (128B swizzle, 16 B atoms): a k-slice of 8 fp32 is 32 bytes inside the 128-byte row; 8-row groups
             // are 1024 B apart (SBO). MN-major (128B swizzle, 32 B atoms): a k-slice is 8 rows of 128 B = two 4-row
             // atoms 512 B apart (SBO); 32-wide MN blocks are one TMA box (4096 B) apart (LBO). The B_lo tile follows
@@ -278,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             auto desc = [](uint32_t hi_word, uint32_t lo_word) { return ((uint64_t)hi_word << 32) | lo_word; };
             int stage = 0, mb = 0;
             uint32_t phase = 0, mphase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = unit; w < total_work; w += num_units) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kc = kb0; kc < kb1; kc += kTcChunk) {
@@ -290,22 +355,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes, b_hi = a_lo + kABytes;
+                        const uint32_t b_lo = b_hi + kBBytes;
                         // low descriptor words: [0,14) start address >> 4, [16,30) LBO >> 4
                         const uint32_t la_hi = ((a_hi >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
                         const uint32_t la_lo = ((a_lo >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
                         const uint32_t lb_hi = ((b_hi >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+                        const uint32_t lb_lo = ((b_lo >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
 #pragma unroll
                         for (int ks = 0; ks < kTcBK / 8; ks++) {
                             const uint64_t da_hi = desc(a_hi_word, la_hi + ks * a_step);
                             const uint64_t da_lo = desc(a_hi_word, la_lo + ks * a_step);
                             const uint64_t db = desc(b_hi_word, lb_hi + ks * b_step);
-                            tc_mma_tf32(tmem_main, da_hi, db, idesc_wide, (kb > kc || ks > 0) ? 1u : 0u);  // [main | corr] (+)= A_hi [B_hi | B_lo]
-                            tc_mma_tf32(tmem_corr, da_lo, db, idesc_half, 1u);                             // corr += A_lo B_hi
+                            const uint32_t first = (kb > kc || ks > 0) ? 1u : 0u;
+                            if constexpr (PAIR) {
+                                // each CTA holds one half of B_hi and of B_lo, so the halves are not adjacent across the
+                                // pair: three M=256 x N=BN products per k-slice (descriptors are CTA-local offsets, valid in both)
+                                const uint64_t db_lo = desc(b_hi_word, lb_lo + ks * b_step);
+                                tc_mma_tf32_pair(tmem_main, da_hi, db, idesc_half, first);     // main (+)= A_hi B_hi
+                                tc_mma_tf32_pair(tmem_corr, da_hi, db_lo, idesc_half, first);  // corr (+)= A_hi B_lo
+                                tc_mma_tf32_pair(tmem_corr, da_lo, db, idesc_half, 1u);        // corr  += A_lo B_hi
+                            } else {
+                                (void)lb_lo;
+                                tc_mma_tf32(tmem_main, da_hi, db, idesc_wide, first);  // [main | corr] (+)= A_hi [B_hi | B_lo]
+                                tc_mma_tf32(tmem_corr, da_lo, db, idesc_half, 1u);     // corr += A_lo B_hi
+                            }
                         }
-                        tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                        // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+                        if constexpr (PAIR) tc_commit_pair(empty_bar(stage));
+                        else tc_commit(empty_bar(stage));
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(main_full_bar(mb));     // chunk complete
+                    if constexpr (PAIR) tc_commit_pair(main_full_bar(mb));  // chunk complete, published to both CTAs
+                    else tc_commit(main_full_bar(mb));
                     if (++mb == 2) { mb = 0; mphase ^= 1; }
                 }
             }
@@ -319,9 +400,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int mb = 0;
         uint32_t mphase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const uint32_t leader_main_empty0 = PAIR ? map_to_cta(main_empty_bar(0), 0) : 0u;
+        const uint32_t leader_main_empty1 = PAIR ? map_to_cta(main_empty_bar(1), 0) : 0u;
+        for (int w = unit; w < total_work; w += num_units) {
             const int tile = w % tiles, split = w / tiles;
-            const int m0 = (tile / sh.num_n_blocks) * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
+            const int m0 = (tile / sh.num_n_blocks) * kTileM + (int)cta_rank * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
             const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < sh.m;
@@ -353,7 +436,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(main_empty_bar(mb));
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster(mb ? leader_main_empty1 : leader_main_empty0);  // the MMA issuer lives in CTA 0
+                    else mbar_arrive(main_empty_bar(mb));
+                }
                 if (++mb == 2) { mb = 0; mphase ^= 1; }
             }
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
@@ -507,10 +593,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (warp >= 4 && lane == 0) tma_store_wait_all();  // staged output tiles must outlive their bulk stores
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's barriers
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     }
 }
 
@@ -581,33 +671,69 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_
 
 static int pick_bn(int n) { return n > 64 ? 128 : (n > 32 ? 64 : 32); }
 
-static int tc_splits(int trans, int m, int n, int k) {
+// CTA-pair mode (cta_group::2, 256 x 128 tiles). Measured at the bench shape (profiles/r1_gemm_tc.md): the split-K
+// wgrad products (long K loops per tile) gain 11 % from the halved B traffic, while the K = 512 forward / dgrad
+// products lose 8 % to the cross-CTA chunk hand-over (4 chunks per tile, three MMA issues per k-slice instead of the
+// 1-CTA kernel's merged two). Default: pairs for the TN products only. FI_TC_PAIR=0 never, =2 always (experiments).
+static int pair_policy() {
+    static const int policy = [] {
+        const char* e = getenv("FI_TC_PAIR");
+        return e ? atoi(e) : 1;
+    }();
+    return policy;
+}
+static bool use_pair(int trans, int m, int n) {
+    const int policy = pair_policy();
+    if (policy == 0 || pick_bn(n) != 128 || m < 2 * kTcBM) return false;
+    return policy >= 2 || trans == 2;
+}
+
+static int tc_splits(int trans, int m, int n, int k, bool pair) {
     if (trans != 2) return 1;
     const int bn = pick_bn(n);
-    const int tiles = ((m + kTcBM - 1) / kTcBM) * ((n + bn - 1) / bn);
+    const int tile_m = pair ? 2 * kTcBM : kTcBM, units = pair ? kNumSMs / 2 : kNumSMs;
+    const int tiles = ((m + tile_m - 1) / tile_m) * ((n + bn - 1) / bn);
     const int num_kb = (k + kTcBK - 1) / kTcBK;
-    int s = kNumSMs / tiles;           // all CTAs of one wave; CTAs of the same split share operand rows in L2
+    int s = units / tiles;               // all CTAs of one wave; CTAs of the same split share operand rows in L2
     if (s > num_kb / 4) s = num_kb / 4;  // at least 4 k-blocks per split
     return s < 1 ? 1 : s;
 }
 
 size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k) {
-    const int s = tc_splits(trans, m, n, k);
+    const int s1 = tc_splits(trans, m, n, k, false), s2 = tc_splits(trans, m, n, k, true);
+    const int s = s1 > s2 ? s1 : s2;     // either mode may be chosen at launch time
     return s > 1 ? (size_t)s * m * n * sizeof(float) : 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEpilogue& ep, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
     const char* label = !B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>");
     LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+    if constexpr (PAIR) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(Cfg::kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;  // the two CTAs of a cluster land on one SM pair
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+    } else {
+        gemm_tc_kernel<BN, A_MN, B_MN, PAIR><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
+                                                                                      maps[5], sh, ep);
+    }
     return ls.done();
 }
 
@@ -620,12 +746,13 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     if (!a.hi || !a.lo || !b.hi || !b.lo || (!out.c && !out.c_hi)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: null operand");
     const bool a_mn = trans == 2, b_mn = trans != 0;
     const int bn = pick_bn(n);
+    const bool pair = use_pair(trans, m, n);
     TcShape sh;
     sh.m = m; sh.n = n; sh.k = k;
-    sh.num_m_blocks = (m + kTcBM - 1) / kTcBM;
+    sh.num_m_blocks = pair ? (m + 2 * kTcBM - 1) / (2 * kTcBM) : (m + kTcBM - 1) / kTcBM;
     sh.num_n_blocks = (n + bn - 1) / bn;
     sh.num_kb = (k + kTcBK - 1) / kTcBK;
-    sh.num_splits = tc_splits(trans, m, n, k);
+    sh.num_splits = tc_splits(trans, m, n, k, pair);
     TcEpilogue ep;
     ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
@@ -656,8 +783,9 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
         FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK, true));
     }
     if (!b_mn) {
-        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn, false));
-        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)bn, false));
+        // K-major B: one box per CTA = its rows of the tile (pair mode: half of them)
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false));
     } else {
         FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
         FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
@@ -674,15 +802,17 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
         if (ep.colsum_out) return set_error(FI_ERR_ARG, "tcgen05 GEMM: fused column sums need the TMA split-output path");
     }
     const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
-    const int grid = total < kNumSMs ? total : kNumSMs;
+    const int units = pair ? kNumSMs / 2 : kNumSMs;
+    const int grid = (total < units ? total : units) * (pair ? 2 : 1);
     int rc;
-#define FI_TC(BNV)                                                                                    \
-    (trans == 0 ? launch_variant<BNV, false, false>(maps, sh, ep, grid, st)                           \
-                : trans == 1 ? launch_variant<BNV, false, true>(maps, sh, ep, grid, st)               \
-                             : launch_variant<BNV, true, true>(maps, sh, ep, grid, st))
-    if (bn == 128) rc = FI_TC(128);
-    else if (bn == 64) rc = FI_TC(64);
-    else rc = FI_TC(32);
+#define FI_TC(BNV, PAIRV)                                                                                    \
+    (trans == 0 ? launch_variant<BNV, false, false, PAIRV>(maps, sh, ep, grid, st)                           \
+                : trans == 1 ? launch_variant<BNV, false, true, PAIRV>(maps, sh, ep, grid, st)               \
+                             : launch_variant<BNV, true, true, PAIRV>(maps, sh, ep, grid, st))
+    if (bn == 128 && pair) rc = FI_TC(128, true);
+    else if (bn == 128) rc = FI_TC(128, false);
+    else if (bn == 64) rc = FI_TC(64, false);
+    else rc = FI_TC(32, false);
 #undef FI_TC
     FI_TRY(rc);
     if (sh.num_splits > 1) {
