@@ -269,24 +269,33 @@ def run_b200_arm(args):
     L.sync(0)
     barrier()
     torch.cuda.synchronize()
-    fi.prof_collect()
-    fi.prof_enable(True)
-    n0 = fi.kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    ev0.record(ext)
-    for i in range(K):
-        device_step(i)
-    ev1.record(ext)
-    L.sync(0)
-    torch.cuda.synchronize()
-    barrier()
-    w1 = time.perf_counter()
-    windows.append((w0, w1))
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = fi.kernel_launch_count() - n0
-    fi.prof_enable(False)
-    prof = fi.prof_collect()
+    def timed_pass(profiled: bool):
+        L.sync(0)
+        barrier()
+        torch.cuda.synchronize()
+        fi.prof_collect()
+        fi.prof_enable(profiled)
+        n0 = fi.kernel_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        ev0.record(ext)
+        for i in range(K):
+            device_step(i)
+        ev1.record(ext)
+        L.sync(0)
+        torch.cuda.synchronize()
+        barrier()
+        windows.append((w0, time.perf_counter()))
+        fi.prof_enable(False)
+        return max_over_ranks(ev0.elapsed_time(ev1)), fi.kernel_launch_count() - n0, fi.prof_collect()
+
+    # Pass 1 is the headline: EXACTLY K steps, two events on the learner's stream, no instrumentation in between.
+    # Pass 2 repeats the same K steps with every launch bracketed by its own event pair (fi_prof_enable) for the per-kernel
+    # rooflines; the ~80 extra event records per step cost about 10 % of a step (tools/host_enqueue.py), which is why the
+    # headline does not come from the instrumented pass. Kernel shares are quoted against pass 2's own step time.
+    ms_total, launches, _ = timed_pass(False)
+    ms_prof_total, _, prof = timed_pass(True)
+    ms_per_step_prof = ms_prof_total / K
     losses = L.last_losses(0)
     ms_per_step = ms_total / K
     value = world * M * T / (ms_per_step / 1e3)
@@ -378,8 +387,9 @@ def run_b200_arm(args):
             peak, unit, bound = peaks["bf16_tflops_sustained"], "TFLOP/s", "tensor"
         kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                          "launches_per_step": r["launches"] / K, "avg_us": avg_ms * 1e3,
-                         "share_of_step": r["total_ms"] / (ms_per_step * K) if world == 1 else None}
-    dominant = max(kernels, key=lambda k: prof[k]["total_ms"]) if kernels else None
+                         "share_of_step": r["total_ms"] / (ms_per_step_prof * K) if world == 1 else None}
+    own = [k for k in kernels if not k.startswith("nccl_")]   # the all-reduce entry is skew + transfer, not one of our kernels
+    dominant = max(own, key=lambda k: prof[k]["total_ms"]) if own else None
     roofline = None
     if dominant:
         d = kernels[dominant]
@@ -421,7 +431,7 @@ def run_b200_arm(args):
                           "parallelism": f"dp{world} (batch sharded, NCCL sum-allreduce of the flat gradient arena)",
                           "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
                           "flops_per_step": None if farmer else 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
-               "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+               "gpu_launches": int(launches), "ms_per_step_instrumented": ms_per_step_prof, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
                "cpu_baseline": cpu, "losses_last_step": [float(x) for x in losses]}
         print(json.dumps(out), flush=True)
     L.close()

@@ -19,7 +19,7 @@ DP_ID_BYTES = 128
 MODEL = {"farmer_lstm": 0, "mlp_actor_critic": 1}
 LOSS = {"mse": 0, "mae": 1, "huber": 2, "vtrace": 3}
 OPT = {"adam": 0, "sgd": 1, "adamw": 2}
-GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
+GEMM = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_f16": 3}
 
 
 class FiBatch(C.Structure):

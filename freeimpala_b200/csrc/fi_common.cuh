@@ -109,6 +109,14 @@ public:
         rec_.b = p.pool[p.used++];
         active_ = cudaEventRecord(rec_.a, st) == cudaSuccess;
     }
+    void done_external() {  // closes a scope around work that is not one of this library's kernels (NCCL): timed, not counted
+        if (active_) {
+            cudaEventRecord(rec_.b, st_);
+            ProfState& p = prof();
+            std::lock_guard<std::mutex> g(p.mu);
+            p.recs.push_back(rec_);
+        }
+    }
     int done() {  // call right after the <<<>>> launch
         const int rc = check_launch(name_);
         if (active_) {

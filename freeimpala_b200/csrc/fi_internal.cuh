@@ -30,23 +30,41 @@ size_t colsum_workspace_bytes(int m, int n);
 // out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).
 int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream);
 
-// ---- tcgen05 3xTF32 path (gemm_tc.cu) -----------------------------------------------------------
-// An fp32 matrix carried as the exact pair x = hi + lo (hi: low 13 mantissa bits cleared), row stride ld.
+// ---- tcgen05 split-operand paths (gemm_tc.cu) ---------------------------------------------------
+// Two operand formats, one kernel:
+//  * 3xTF32: an fp32 matrix carried as the exact pair x = hi + lo (hi: low 13 mantissa bits cleared), both fp32 arrays;
+//  * 3xFP16 (hs != nullptr): x * scale = hi + lo' / 2048 with hi, lo' fp16 arrays and `scale` a power of two kept in a
+//    device-resident HScale next to the tensor's measured max |x|. kind::f16 MMAs run at twice the kind::tf32 rate on
+//    half the shared-memory bytes per reduction element, and fp16 carries the same 11 significant bits as TF32.
+struct HScale {    // device memory, one per split tensor
+    float scale;   // power of two applied before the fp16 split
+    float inv;     // 1 / scale
+    float amax;    // max |x| in true units (atomicMax over the bit pattern; zero it before the producer runs)
+    float bound;   // the a-priori bound the scale was derived from (diagnostics)
+};
 struct SplitMat {
-    const float* hi;
-    const float* lo;
-    int ld;
+    const void* hi;  // float (3xTF32) or __half (3xFP16)
+    const void* lo;
+    int ld;          // row stride in elements
+    const HScale* hs = nullptr;  // non-null selects the fp16 format
 };
 struct TcOut {
     float* c; int ldc;                       // plain fp32 output (may be null)
-    float* c_hi; float* c_lo; int ld_split;  // hi/lo output for the next GEMM (may be null)
+    void* c_hi; void* c_lo; int ld_split;    // hi/lo output for the next GEMM (may be null); element type as the operands
     int transpose;                           // plain output written as c[col * ldc + row]
     const uint32_t* mask_bits_in;            // bit-packed ReLU decisions applied to the output (backward), or null
     uint32_t* mask_bits_out;                 // bit-packed (output > 0) written by a ReLU epilogue (forward), or null
     int mask_ldw;                            // words per mask row (a multiple of 4)
     float* colsum_out;                       // [4 * ceil(m/128), n] per-32-row column sums of the output (split-output path), or null
+    HScale* out_hs = nullptr;                // fp16 format with a split output: receives the output's scale and max |x|
+    const HScale* bias_hs = nullptr;         // fp16 format: a tensor whose amax bounds |bias| (the parameter arena)
 };
 int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st);
+// fp16 format pre-passes: amax accumulates max |x| into hs->amax; split derives the scale from hs->amax (which must
+// bound the matrix) and writes hi / lo' with columns [cols, ld_out) zero-filled. write_scale: publish scale/inv in *hs.
+int launch_amax(const float* x, int ld_in, size_t rows, int cols, HScale* hs, cudaStream_t st);
+int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, int write_scale,
+                   cudaStream_t st);
 int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,
                          const float* mask, int ldmask, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k);

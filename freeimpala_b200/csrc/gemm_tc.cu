@@ -31,25 +31,29 @@
 // supports the 128B swizzle with 32-byte atoms there), so dgrad (B = W[n,k] read along n) and wgrad (both operands
 // read along the batch rows) need no transposed copies.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "fi_internal.cuh"
 
 namespace fi {
 
 constexpr int kTcBM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
-constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int kTcRowBytes = 128;     // one k-block of one matrix row = 128 bytes = one swizzle row:
+constexpr int kTcBK = 32;            //   32 fp32 (3xTF32) or
+constexpr int kTcBKh = 64;           //   64 fp16 (3xFP16) reduction elements
 constexpr int kTcCtrlThreads = 128;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, (idle)
-constexpr int kTcChunk = 4;      // k-blocks accumulated in TMEM before promotion to registers (16 wide MMAs)
+constexpr int kTcChunkK = 128;       // reduction elements accumulated in TMEM before promotion to registers (16 wide MMAs)
 constexpr int kTcSmemLimit = 227 * 1024;
 
 struct TcEpilogue {
     float* c;            // plain fp32 output (may be null)
     int ldc;
-    float* c_hi;         // split output (may be null)
-    float* c_lo;
+    void* c_hi;          // split output (may be null): float or __half arrays, as the operands
+    void* c_lo;
     int ldc_split;
     const float* bias;   // [n] or null
     const float* mask;   // [m, ldmask]: out = mask > 0 ? out : 0 (ReLU backward), or null
@@ -62,6 +66,11 @@ struct TcEpilogue {
     int tma_split;       // c_hi / c_lo are written with TMA stores (map_c_hi / map_c_lo are valid)
     float* colsum_out;   // [4 * num_m_blocks, n]: column sums of the output over each warp's 32 rows (bias gradient), or null
     size_t split_stride; // elements between split-K slabs of c
+    // 3xFP16 format only
+    const HScale* a_hs;  // operand scales: the accumulator is (A * sa)(B * sb), multiplied by inv_a * inv_b on the way out
+    const HScale* b_hs;
+    const HScale* bias_hs;  // bounds |bias| (null without bias)
+    HScale* out_hs;      // split output: scale derived from k * amax_a * amax_b (+ amax_bias); amax measured by the epilogue
 };
 
 struct TcShape {
@@ -107,6 +116,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -164,6 +176,23 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -188,10 +217,40 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms)
     return d;
 }
-// tcgen05 instruction descriptor: D fp32, A/B tf32, dense (cute::UMMA::InstrDescriptor bit layout).
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// tcgen05 instruction descriptor: D fp32, A/B tf32 (format 2) or fp16 (format 0), dense (cute::UMMA::InstrDescriptor bit layout).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major, int half) {
+    const uint32_t fmt = half ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Scale of a 3xFP16 tensor bounded by `bound`: the power of two that puts the bound in (2^13, 2^14], a factor 4 under the
+// fp16 maximum (the bound is computed in fp32 and the data it bounds carry fp32 rounding). hi and lo' then resolve
+// 2^-36 absolutely and 2^-22 relatively, i.e. tensors whose true maximum sits up to ~2^27 below the bound keep fp32-level
+// accuracy in the norm-wise sense that matters for a dot product.
+__host__ __device__ __forceinline__ float hscale_from_bound(float bound) {
+    if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+    int ex;
+    frexpf(bound, &ex);                 // bound = f * 2^ex, f in [0.5, 1)
+    int e = 14 - ex;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    return ldexpf(1.f, e);
+}
+// column sums of a 32 x 32 block held one row per lane (x[i] = column i of this lane's row) by recursive halving: after the
+// step with offset o a lane keeps the half of its columns selected by its bit o, summed with its partner's; 31 shuffles, and
+// lane j returns the sum of column j.
+__device__ __forceinline__ float warp_colsum32(const float* x, int lane) {
+    float y16[16], y8[8], y4[4], y2[2];
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) y16[i] = (b16 ? x[16 + i] : x[i]) + __shfl_xor_sync(0xFFFFFFFFu, b16 ? x[i] : x[16 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 8; i++) y8[i] = (b8 ? y16[8 + i] : y16[i]) + __shfl_xor_sync(0xFFFFFFFFu, b8 ? y16[i] : y16[8 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) y4[i] = (b4 ? y8[4 + i] : y8[i]) + __shfl_xor_sync(0xFFFFFFFFu, b4 ? y8[i] : y8[4 + i], 4);
+#pragma unroll
+    for (int i = 0; i < 2; i++) y2[i] = (b2 ? y4[2 + i] : y4[i]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? y4[i] : y4[2 + i], 2);
+    return (b1 ? y2[1] : y2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? y2[0] : y2[1], 1);
 }
 
 // PAIR: two CTAs of a cluster (one SM pair) work on one 256 x BN tile with cta_group::2 MMAs. Each CTA holds its own
@@ -200,7 +259,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, 
 template <int BN, bool PAIR = false>
 struct TcCfg {
     static constexpr int kBRows = PAIR ? BN / 2 : BN;                 // rows of the B tile held by one CTA
-    static constexpr int kStageBytes = 2 * (kTcBM + kBRows) * kTcBK * 4;  // A_hi, A_lo, B_hi, B_lo
+    static constexpr int kStageBytes = 2 * (kTcBM + kBRows) * kTcRowBytes;  // A_hi, A_lo, B_hi, B_lo
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static_assert(!PAIR || BN == 128, "pair mode is built for BN = 128");
     static constexpr int kStages = PAIR ? 4 : (BN >= 128 ? 3 : 4);
@@ -217,7 +276,8 @@ struct TcCfg {
 };
 
 // One kernel for the three operand-major combinations. A_MN / B_MN: operand is MN-major (reduction index slow).
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+// H: 3xFP16 operand format (fp16 hi / lo' pairs with per-tensor scales) instead of 3xTF32.
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H>
 __global__ void __launch_bounds__(TcCfg<BN, PAIR>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -225,13 +285,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const TcShape sh, const TcEpilogue ep) {
     using Cfg = TcCfg<BN, PAIR>;
     constexpr int kStages = Cfg::kStages;
-    constexpr uint32_t kABytes = kTcBM * kTcBK * 4;   // one of A_hi / A_lo
-    constexpr uint32_t kBBytes = Cfg::kBRows * kTcBK * 4;
+    static_assert(!H || BN >= 64, "the fp16 format needs 64-wide MN blocks");
+    constexpr int BK = H ? kTcBKh : kTcBK;            // reduction elements per k-block
+    constexpr int kChunk = kTcChunkK / BK;            // k-blocks per TMEM chunk
+    constexpr int kBoxMN = H ? 64 : 32;               // MN extent of one MN-major box (128 bytes)
+    constexpr uint32_t kABytes = kTcBM * kTcRowBytes; // one of A_hi / A_lo
+    constexpr uint32_t kBBytes = Cfg::kBRows * kTcRowBytes;
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
     const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // CTA (or CTA pair) index
     const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int kTileM = PAIR ? 2 * kTcBM : kTcBM;
-    constexpr uint32_t kBoxBytes = 32 * kTcBK * 4;    // one MN-major box: 32 k-rows x 128 B
+    constexpr uint32_t kBoxBytes = BK * kTcRowBytes;  // one MN-major box: BK k-rows x 128 B
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
     // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2]
@@ -244,6 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto main_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float tmax_kernel = 0.f;  // fp16 format: running max |output| of this thread (published once at the end)
     const int tiles = sh.num_m_blocks * sh.num_n_blocks;
     const int total_work = tiles * sh.num_splits;
 
@@ -300,15 +365,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (!PAIR || cta_rank == 0) mbar_expect_tx(bar, (PAIR ? 2 : 1) * Cfg::kStageBytes);
                     const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
                     const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
-                    const int k0 = kb * kTcBK;
+                    const int k0 = kb * BK;
                     if constexpr (!A_MN) {
                         load(a_hi, &map_a_hi, bar, k0, m0);
                         load(a_lo, &map_a_lo, bar, k0, m0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < kTcBM / 32; j++) {
-                            load(a_hi + j * kBoxBytes, &map_a_hi, bar, m0 + j * 32, k0);
-                            load(a_lo + j * kBoxBytes, &map_a_lo, bar, m0 + j * 32, k0);
+                        for (int j = 0; j < kTcBM / kBoxMN; j++) {
+                            load(a_hi + j * kBoxBytes, &map_a_hi, bar, m0 + j * kBoxMN, k0);
+                            load(a_lo + j * kBoxBytes, &map_a_lo, bar, m0 + j * kBoxMN, k0);
                         }
                     }
                     if constexpr (!B_MN) {
@@ -316,9 +381,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         load(b_lo, &map_b_lo, bar, k0, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < Cfg::kBRows / 32; j++) {
-                            load(b_hi + j * kBoxBytes, &map_b_hi, bar, n0 + j * 32, k0);
-                            load(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * 32, k0);
+                        for (int j = 0; j < Cfg::kBRows / kBoxMN; j++) {
+                            load(b_hi + j * kBoxBytes, &map_b_hi, bar, n0 + j * kBoxMN, k0);
+                            load(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * kBoxMN, k0);
                         }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -328,29 +393,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t idesc_wide = umma_idesc(kTcBM, 2 * BN, A_MN ? 1 : 0, B_MN ? 1 : 0);  // A_hi [B_hi | B_lo]
-            constexpr uint32_t idesc_half = umma_idesc(kTileM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);      // A_lo B_hi (pair: every product)
+            constexpr uint32_t idesc_wide = umma_idesc(kTcBM, 2 * BN, A_MN ? 1 : 0, B_MN ? 1 : 0, H ? 1 : 0);  // A_hi [B_hi | B_lo]
+            constexpr uint32_t idesc_half = umma_idesc(kTileM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, H ? 1 : 0);      // A_lo B_hi (pair: every product)
             // K-major (128B swizzle, 16 B atoms): a k-slice of 8 fp32 is 32 bytes inside the 128-byte row; 8-row groups
             // are 1024 B apart (SBO). MN-major (128B swizzle, 32 B atoms): a k-slice is 8 rows of 128 B = two 4-row
             // atoms 512 B apart (SBO); 32-wide MN blocks are one TMA box (4096 B) apart (LBO). The B_lo tile follows
             // the B_hi tile with the same strides, so a descriptor at B_hi with N = 2*BN covers both.
-            constexpr uint32_t a_step = (A_MN ? 1024u : 32u) >> 4, b_step = (B_MN ? 1024u : 32u) >> 4;
+            // fp16 format: a k-slice is 16 halves = the same 32 bytes of a K-major row; MN-major tiles use the plain
+            // 128B swizzle (16 B atoms) in boxes of [64 k][64 mn]: a k-slice is 16 rows = two 8-row groups 1024 B apart
+            // (SBO), 64-wide MN blocks are one box (8192 B) apart (LBO).
+            constexpr uint32_t kMnStep = H ? 2048u : 1024u, kMnSbo = H ? 1024u : 512u, kMnType = H ? 2u : 1u;
+            constexpr uint32_t a_step = (A_MN ? kMnStep : 32u) >> 4, b_step = (B_MN ? kMnStep : 32u) >> 4;
             constexpr uint32_t a_lbo = A_MN ? kBoxBytes : 0u, b_lbo = B_MN ? kBoxBytes : 0u;
-            constexpr uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+            constexpr uint32_t a_sbo = A_MN ? kMnSbo : 1024u, b_sbo = B_MN ? kMnSbo : 1024u;
             // descriptor words that never change: [32,46) SBO, [46,48) version 1, [61,64) layout type
-            constexpr uint32_t a_hi_word = (a_sbo >> 4) | (1u << 14) | ((A_MN ? 1u : 2u) << 29);
-            constexpr uint32_t b_hi_word = (b_sbo >> 4) | (1u << 14) | ((B_MN ? 1u : 2u) << 29);
+            constexpr uint32_t a_hi_word = (a_sbo >> 4) | (1u << 14) | ((A_MN ? kMnType : 2u) << 29);
+            constexpr uint32_t b_hi_word = (b_sbo >> 4) | (1u << 14) | ((B_MN ? kMnType : 2u) << 29);
+            auto mma = [](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+                if constexpr (PAIR) {
+                    if constexpr (H) tc_mma_f16_pair(d, da, db, idesc, accumulate);
+                    else tc_mma_tf32_pair(d, da, db, idesc, accumulate);
+                } else {
+                    if constexpr (H) tc_mma_f16(d, da, db, idesc, accumulate);
+                    else tc_mma_tf32(d, da, db, idesc, accumulate);
+                }
+            };
             auto desc = [](uint32_t hi_word, uint32_t lo_word) { return ((uint64_t)hi_word << 32) | lo_word; };
             int stage = 0, mb = 0;
             uint32_t phase = 0, mphase = 0;
             for (int w = unit; w < total_work; w += num_units) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
-                for (int kc = kb0; kc < kb1; kc += kTcChunk) {
+                for (int kc = kb0; kc < kb1; kc += kChunk) {
                     mbar_wait(main_empty_bar(mb), mphase ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_main = tmem_base + (uint32_t)(mb * 2 * BN), tmem_corr = tmem_main + BN;
-                    const int kce = min(kb1, kc + kTcChunk);
+                    const int kce = min(kb1, kc + kChunk);
                     for (int kb = kc; kb < kce; kb++) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
@@ -362,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint32_t lb_hi = ((b_hi >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
                         const uint32_t lb_lo = ((b_lo >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
 #pragma unroll
-                        for (int ks = 0; ks < kTcBK / 8; ks++) {
+                        for (int ks = 0; ks < 4; ks++) {  // 4 k-slices of 32 bytes (8 tf32 / 16 fp16) per k-block
                             const uint64_t da_hi = desc(a_hi_word, la_hi + ks * a_step);
                             const uint64_t da_lo = desc(a_hi_word, la_lo + ks * a_step);
                             const uint64_t db = desc(b_hi_word, lb_hi + ks * b_step);
@@ -371,13 +449,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 // each CTA holds one half of B_hi and of B_lo, so the halves are not adjacent across the
                                 // pair: three M=256 x N=BN products per k-slice (descriptors are CTA-local offsets, valid in both)
                                 const uint64_t db_lo = desc(b_hi_word, lb_lo + ks * b_step);
-                                tc_mma_tf32_pair(tmem_main, da_hi, db, idesc_half, first);     // main (+)= A_hi B_hi
-                                tc_mma_tf32_pair(tmem_corr, da_hi, db_lo, idesc_half, first);  // corr (+)= A_hi B_lo
-                                tc_mma_tf32_pair(tmem_corr, da_lo, db, idesc_half, 1u);        // corr  += A_lo B_hi
+                                mma(tmem_main, da_hi, db, idesc_half, first);     // main (+)= A_hi B_hi
+                                mma(tmem_corr, da_hi, db_lo, idesc_half, first);  // corr (+)= A_hi B_lo
+                                mma(tmem_corr, da_lo, db, idesc_half, 1u);        // corr  += A_lo B_hi
                             } else {
                                 (void)lb_lo;
-                                tc_mma_tf32(tmem_main, da_hi, db, idesc_wide, first);  // [main | corr] (+)= A_hi [B_hi | B_lo]
-                                tc_mma_tf32(tmem_corr, da_lo, db, idesc_half, 1u);     // corr += A_lo B_hi
+                                mma(tmem_main, da_hi, db, idesc_wide, first);  // [main | corr] (+)= A_hi [B_hi | B_lo]
+                                mma(tmem_corr, da_lo, db, idesc_half, 1u);     // corr += A_lo B_hi
                             }
                         }
                         // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
@@ -402,6 +480,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t mphase = 0;
         const uint32_t leader_main_empty0 = PAIR ? map_to_cta(main_empty_bar(0), 0) : 0u;
         const uint32_t leader_main_empty1 = PAIR ? map_to_cta(main_empty_bar(1), 0) : 0u;
+        // fp16 format: corr carries lo' = 2048 lo; the accumulator is in units of scale_a * scale_b
+        constexpr float kCorrMul = H ? (1.f / 2048.f) : 1.f;
+        float out_mul = 1.f, out_scale = 1.f;
+        if constexpr (H) {
+            out_mul = ep.a_hs->inv * ep.b_hs->inv;
+            if (ep.out_hs) {
+                const float bound = (float)sh.k * ep.a_hs->amax * ep.b_hs->amax + (ep.bias_hs ? ep.bias_hs->amax : 0.f);
+                out_scale = hscale_from_bound(bound);
+                if (blockIdx.x == 0 && threadIdx.x == kTcCtrlThreads) {
+                    ep.out_hs->scale = out_scale;
+                    ep.out_hs->inv = 1.f / out_scale;
+                    ep.out_hs->bound = bound;
+                }
+            }
+        }
         for (int w = unit; w < total_work; w += num_units) {
             const int tile = w % tiles, split = w / tiles;
             const int m0 = (tile / sh.num_n_blocks) * kTileM + (int)cta_rank * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
@@ -421,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int c = 0; c < CW / 32; c++)
                     if (n0 + nc0 + c * 32 < sh.n) mw[c] = __ldg(ep.mask_bits + (size_t)row * ep.mask_ldw + ((n0 + nc0) >> 5) + c);
             }
-            for (int kc = kb0; kc < kb1; kc += kTcChunk) {
+            for (int kc = kb0; kc < kb1; kc += kChunk) {
                 mbar_wait(main_full_bar(mb), mphase);
                 tc_fence_after();
 #pragma unroll
@@ -432,7 +525,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i++)  // round-to-nearest promotion
-                        acc[c * 32 + i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        acc[c * 32 + i] += H ? fmaf(__uint_as_float(u[i]), kCorrMul, __uint_as_float(v[i]))
+                                             : __uint_as_float(v[i]) + __uint_as_float(u[i]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -441,6 +535,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     else mbar_arrive(main_empty_bar(mb));
                 }
                 if (++mb == 2) { mb = 0; mphase ^= 1; }
+            }
+            if constexpr (H) {
+#pragma unroll
+                for (int i = 0; i < CW; i++) acc[i] *= out_mul;   // powers of two: exact
             }
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
             if (ep.transpose_out) {
@@ -464,7 +562,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     for (int i = 0; i < 32; i++) acc[c * 32 + i] = ((mw[c] >> i) & 1u) ? acc[c * 32 + i] : 0.f;
                 }
             }
-            if (ep.tma_split) {
+            if constexpr (H) {
+                if (ep.tma_split) {
+                    // fp16 pair output (BN = 128: this warp owns 64 columns = one 128-byte row of halves per matrix row)
+                    if constexpr (CW == 64) {
+                        const uint32_t stage_tile = out_tiles + (uint32_t)pw * 4096u;  // 32 x 128 B, reused for hi then lo'
+                        const int rbase = m0 + q * 32, colw0 = n0 + nc0;
+                        if (colw0 < sh.n) {  // warp-uniform
+#pragma unroll
+                            for (int c = 0; c < 2; c++) {
+                                const int col0 = colw0 + c * 32;
+                                uint32_t bits = 0;
+#pragma unroll
+                                for (int i = 0; i < 32; i++) {
+                                    float t = acc[c * 32 + i];
+                                    if (ep.bias && col0 + i < sh.n) t += __ldg(ep.bias + col0 + i);
+                                    if (ep.relu) t = fmaxf(t, 0.f);
+                                    bits |= (t > 0.f ? 1u : 0u) << i;
+                                    acc[c * 32 + i] = t;
+                                    tmax_kernel = fmaxf(tmax_kernel, fabsf(t));
+                                }
+                                if (col0 < sh.n) {
+                                    if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
+                                    if (ep.colsum_out) {
+                                        const float y1 = warp_colsum32(acc + c * 32, lane);
+                                        if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int part = 0; part < 2; part++) {
+                                if (lane == 0) tma_store_wait_read();
+                                __syncwarp();
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {   // 16-byte chunk j = columns 8j .. 8j+7
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {
+                                        const float s0 = acc[8 * j + 2 * e] * out_scale, s1 = acc[8 * j + 2 * e + 1] * out_scale;
+                                        __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+                                        if (part == 1) {
+                                            h0 = __float2half_rn((s0 - __half2float(h0)) * 2048.f);
+                                            h1 = __float2half_rn((s1 - __half2float(h1)) * 2048.f);
+                                        }
+                                        w[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                    }
+                                    st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
+                                                  make_uint4(w[0], w[1], w[2], w[3]));  // 128B swizzle
+                                }
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(part == 0 ? &map_c_hi : &map_c_lo, stage_tile, colw0, rbase);
+                                    tma_store_commit();
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
+            }
+            if (!H && ep.tma_split) {
                 // hi/lo pair output: bias, ReLU, the split and the ReLU bit mask are computed in registers (lane = row),
                 // the 32 x 32 block goes to this warp's 128B-swizzled staging tiles with conflict-free 16-byte stores, and
                 // one lane hands both tiles to the TMA (cp.async.bulk.tensor store): no per-element address arithmetic
@@ -488,20 +646,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
                     if (ep.colsum_out) {
-                        // column sums over this warp's 32 rows by recursive halving: after the step with offset o a lane keeps
-                        // the half of its columns selected by its bit o, summed with its partner's; 31 shuffles, and lane j
-                        // ends up with the sum of column j. Rows beyond m contribute exact zeros (zero-filled A rows).
-                        float y16[16], y8[8], y4[4], y2[2];
-                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) y16[i] = (b16 ? x[16 + i] : x[i]) + __shfl_xor_sync(0xFFFFFFFFu, b16 ? x[i] : x[16 + i], 16);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) y8[i] = (b8 ? y16[8 + i] : y16[i]) + __shfl_xor_sync(0xFFFFFFFFu, b8 ? y16[i] : y16[8 + i], 8);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) y4[i] = (b4 ? y8[4 + i] : y8[i]) + __shfl_xor_sync(0xFFFFFFFFu, b4 ? y8[i] : y8[4 + i], 4);
-#pragma unroll
-                        for (int i = 0; i < 2; i++) y2[i] = (b2 ? y4[2 + i] : y4[i]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? y4[i] : y4[2 + i], 2);
-                        const float y1 = (b1 ? y2[1] : y2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? y2[0] : y2[1], 1);
+                        // column sums over this warp's 32 rows; rows beyond m contribute exact zeros (zero-filled A rows)
+                        const float y1 = warp_colsum32(x, lane);
                         if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
                     }
                     // hi tile, then lo tile, through the same staging buffer: the sibling warp on this scheduler runs while
@@ -550,8 +696,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const bool col_ok = col < sh.n;
                 const float bias = (ep.bias && col_ok) ? __ldg(ep.bias + col) : 0.f;
                 float* pc = cplain ? cplain + (size_t)rbase * ep.ldc + col : nullptr;
-                float* ph = ep.c_hi ? ep.c_hi + (size_t)rbase * ep.ldc_split + col : nullptr;
-                float* pl = ep.c_hi ? ep.c_lo + (size_t)rbase * ep.ldc_split + col : nullptr;
+                float* ph = (!H && ep.c_hi) ? static_cast<float*>(ep.c_hi) + (size_t)rbase * ep.ldc_split + col : nullptr;
+                float* pl = (!H && ep.c_hi) ? static_cast<float*>(ep.c_lo) + (size_t)rbase * ep.ldc_split + col : nullptr;
                 const float* pm = ep.mask ? ep.mask + (size_t)rbase * ep.ldmask + col : nullptr;
                 uint32_t myword = 0;
 #pragma unroll 1
@@ -591,6 +737,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     }
 
+    if constexpr (H) {
+        if (warp >= 4 && ep.out_hs) {  // max |output| over everything this warp produced: one atomic per warp
+            const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(tmax_kernel));
+            if (lane == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&ep.out_hs->amax), wm);
+        }
+    }
     if (warp >= 4 && lane == 0) tma_store_wait_all();  // staged output tiles must outlive their bulk stores
     tc_fence_before();
     if constexpr (PAIR) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's barriers
@@ -630,6 +782,65 @@ int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_o
     return ls.done();
 }
 
+// ---- 3xFP16 pre-passes ---------------------------------------------------------------------------------------
+// max |x| over a [rows, cols] matrix (row stride ld_in) into hs->amax. Non-negative floats order like their bit patterns.
+__global__ void amax_kernel(const float* __restrict__ x, int ld_in, size_t rows, int cols, HScale* hs) {
+    const size_t total = rows * (size_t)cols;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / cols;
+        m = fmaxf(m, fabsf(__ldg(x + r * ld_in + (i - r * cols))));
+    }
+    const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&hs->amax), wm);
+}
+
+int launch_amax(const float* x, int ld_in, size_t rows, int cols, HScale* hs, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return FI_OK;
+    const size_t total = rows * (size_t)cols;
+    size_t blocks = (total + 1023) / 1024;
+    if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+    LaunchScope ls("amax_kernel", st, 4.0 * (double)total, kWorkBytes);
+    amax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, hs);
+    return ls.done();
+}
+
+// fp32 -> fp16 (hi, lo') pair of x * scale, scale = hscale_from_bound(hs->amax): dense [rows, ld_out] arrays (ld_out even),
+// columns [cols, ld_out) zero-filled. Two elements per thread (one 4-byte store per array). Traffic 4 + 4 B per element.
+__global__ void split_h_kernel(const float* __restrict__ x, int ld_in, size_t rows, int cols, int ld_out, __half2* __restrict__ hi,
+                               __half2* __restrict__ lo, HScale* hs, int write_scale) {
+    const float scale = hscale_from_bound(hs->amax);
+    if (write_scale && blockIdx.x == 0 && threadIdx.x == 0) {
+        hs->scale = scale;
+        hs->inv = 1.f / scale;
+        hs->bound = hs->amax;
+    }
+    const int ldp = ld_out >> 1;
+    const size_t total = rows * (size_t)ldp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / ldp;
+        const int c = (int)(i - r * ldp) * 2;
+        const float v0 = c < cols ? __ldg(x + r * ld_in + c) * scale : 0.f;
+        const float v1 = c + 1 < cols ? __ldg(x + r * ld_in + c + 1) * scale : 0.f;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        hi[i] = __halves2half2(h0, h1);
+        lo[i] = __halves2half2(__float2half_rn((v0 - __half2float(h0)) * 2048.f), __float2half_rn((v1 - __half2float(h1)) * 2048.f));
+    }
+}
+
+int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, int write_scale,
+                   cudaStream_t st) {
+    if (rows == 0 || ld_out == 0) return FI_OK;
+    if (ld_out & 1) return set_error(FI_ERR_ARG, "split_h: ld_out must be even");
+    const size_t total = rows * (size_t)(ld_out / 2);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    LaunchScope ls("split_h_kernel", st, 4.0 * (double)rows * cols + 4.0 * (double)rows * ld_out, kWorkBytes);
+    split_h_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, ld_out, static_cast<__half2*>(hi), static_cast<__half2*>(lo), hs,
+                                                     write_scale);
+    return ls.done();
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -651,25 +862,72 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row stride ld elements;
 // box = 32 inner elements (128 B, the swizzle span) x box_outer rows. Out-of-bounds elements read as zero.
-static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
-                    bool mn_major) {
+// Encoding a tensor map is a driver call (a few microseconds); a learner step needs ~100 of them and always the same
+// ones (fixed buffers, fixed shapes), so they are cached by their defining tuple. With 8 ranks sharing 16 host cores the
+// step was host-enqueue bound before this cache (profiles/r1_bench_8gpu.json: 0.96 ms of gaps per 5.3 ms step).
+struct MapKey {
+    const void* base;
+    uint64_t inner, outer, ld;
+    uint32_t box_outer, mn_major;  // mn_major: bit 0 = MN-major operand, bit 1 = fp16 elements
+    bool operator==(const MapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer && mn_major == o.mn_major;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.inner + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= (k.outer * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        h ^= (k.ld * 0x165667B19E3779F9ull) ^ ((uint64_t)k.box_outer << 33) ^ k.mn_major;
+        return (size_t)h;
+    }
+};
+
+static int make_map_uncached(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                             bool mn_major, bool half);
+
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                    bool mn_major, bool half = false) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{base, inner, outer, ld, box_outer, (mn_major ? 1u : 0u) | (half ? 2u : 0u)};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *map = it->second;
+            return FI_OK;
+        }
+    }
+    FI_TRY(make_map_uncached(map, base, inner, outer, ld, box_outer, mn_major, half));
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();  // operator-level callers with ever-changing buffers: bound the table
+    cache.emplace(key, *map);
+    return FI_OK;
+}
+
+static int make_map_uncached(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                             bool mn_major, bool half) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16)
+    const uint64_t esz = half ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * esz) % 16)
         return set_error(FI_ERR_ARG, "tcgen05 GEMM: operand base / row stride must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * 4};
-    cuuint32_t box[2] = {32, box_outer};
+    cuuint64_t strides[1] = {ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_outer};   // 128 bytes of the contiguous dimension = the swizzle span
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+    // MN-major tf32 operands only exist with 32-byte swizzle atoms; fp16 uses the plain 128B swizzle for both majors
+    CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    (mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FI_OK;
 }
 
-static int pick_bn(int n) { return n > 64 ? 128 : (n > 32 ? 64 : 32); }
+static int pick_bn(int n, bool half = false) { return n > 64 ? 128 : ((n > 32 || half) ? 64 : 32); }
 
 // CTA-pair mode (cta_group::2, 256 x 128 tiles). Measured at the bench shape (profiles/r1_gemm_tc.md): the split-K
 // wgrad products (long K loops per tile) gain 11 % from the halved B traffic, while the K = 512 forward / dgrad
@@ -688,33 +946,39 @@ static bool use_pair(int trans, int m, int n) {
     return policy >= 2 || trans == 2;
 }
 
-static int tc_splits(int trans, int m, int n, int k, bool pair) {
+static int tc_splits(int trans, int m, int n, int k, bool pair, bool half = false) {
     if (trans != 2) return 1;
-    const int bn = pick_bn(n);
+    const int bn = pick_bn(n, half);
     const int tile_m = pair ? 2 * kTcBM : kTcBM, units = pair ? kNumSMs / 2 : kNumSMs;
     const int tiles = ((m + tile_m - 1) / tile_m) * ((n + bn - 1) / bn);
-    const int num_kb = (k + kTcBK - 1) / kTcBK;
+    const int bk = half ? kTcBKh : kTcBK;
+    const int num_kb = (k + bk - 1) / bk;
     int s = units / tiles;               // all CTAs of one wave; CTAs of the same split share operand rows in L2
     if (s > num_kb / 4) s = num_kb / 4;  // at least 4 k-blocks per split
     return s < 1 ? 1 : s;
 }
 
 size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k) {
-    const int s1 = tc_splits(trans, m, n, k, false), s2 = tc_splits(trans, m, n, k, true);
-    const int s = s1 > s2 ? s1 : s2;     // either mode may be chosen at launch time
+    int s = 1;                           // either CTA mode and either operand format may be chosen at launch time
+    for (int pair = 0; pair < 2; pair++)
+        for (int half = 0; half < 2; half++) {
+            const int v = tc_splits(trans, m, n, k, pair != 0, half != 0);
+            if (v > s) s = v;
+        }
     return s > 1 ? (size_t)s * m * n * sizeof(float) : 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H>
 static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEpilogue& ep, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
-    const char* label = !B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>");
+    const char* label = H ? (!B_MN ? "gemm_tc_kernel<f16x3,NT>" : (!A_MN ? "gemm_tc_kernel<f16x3,NN>" : "gemm_tc_kernel<f16x3,TN>"))
+                          : (!B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>"));
     LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
     if constexpr (PAIR) {
         cudaLaunchConfig_t cfg = {};
@@ -729,9 +993,9 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
     } else {
-        gemm_tc_kernel<BN, A_MN, B_MN, PAIR><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
+        gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
                                                                                       maps[5], sh, ep);
     }
     return ls.done();
@@ -745,19 +1009,24 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     if (trans < 0 || trans > 2) return set_error(FI_ERR_ARG, "gemm: trans must be 0, 1 or 2");
     if (!a.hi || !a.lo || !b.hi || !b.lo || (!out.c && !out.c_hi)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: null operand");
     const bool a_mn = trans == 2, b_mn = trans != 0;
-    const int bn = pick_bn(n);
+    const bool half = a.hs != nullptr;
+    if (half != (b.hs != nullptr)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: operands are in different split formats");
+    const int bn = pick_bn(n, half), bk = half ? kTcBKh : kTcBK;
     const bool pair = use_pair(trans, m, n);
     TcShape sh;
     sh.m = m; sh.n = n; sh.k = k;
     sh.num_m_blocks = pair ? (m + 2 * kTcBM - 1) / (2 * kTcBM) : (m + kTcBM - 1) / kTcBM;
     sh.num_n_blocks = (n + bn - 1) / bn;
-    sh.num_kb = (k + kTcBK - 1) / kTcBK;
-    sh.num_splits = tc_splits(trans, m, n, k, pair);
+    sh.num_kb = (k + bk - 1) / bk;
+    sh.num_splits = tc_splits(trans, m, n, k, pair, half);
     TcEpilogue ep;
     ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
     ep.mask_bits = out.mask_bits_in; ep.mask_bits_out = out.mask_bits_out; ep.mask_ldw = out.mask_ldw;
     ep.colsum_out = out.colsum_out;
+    ep.a_hs = a.hs; ep.b_hs = b.hs; ep.bias_hs = bias ? out.bias_hs : nullptr; ep.out_hs = out.c_hi ? out.out_hs : nullptr;
+    if (half && out.c_hi && (!out.out_hs || (bias && !out.bias_hs) || bn != 128))
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM (fp16 format): a split output needs n > 64, its HScale and a bound for the bias");
     if (ep.colsum_out && (bias || relu)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: fused column sums exclude bias/ReLU");
     if (ep.mask_bits && (bias || relu || (n > 32 && (ep.mask_ldw % 4 || (reinterpret_cast<uintptr_t>(ep.mask_bits) & 15)))))
         return set_error(FI_ERR_ARG, "tcgen05 GEMM: a bit mask excludes bias/ReLU and needs 16-byte aligned rows");
@@ -776,43 +1045,49 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     sh.num_splits = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;
     CUtensorMap maps[6];
     if (!a_mn) {
-        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
-        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false));
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false, half));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)k, (uint64_t)m, (uint64_t)a.ld, kTcBM, false, half));
     } else {
-        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK, true));
-        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, kTcBK, true));
+        FI_TRY(make_map(&maps[0], a.hi, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, (uint32_t)bk, true, half));
+        FI_TRY(make_map(&maps[1], a.lo, (uint64_t)m, (uint64_t)k, (uint64_t)a.ld, (uint32_t)bk, true, half));
     }
     if (!b_mn) {
         // K-major B: one box per CTA = its rows of the tile (pair mode: half of them)
-        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false));
-        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false));
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false, half));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)k, (uint64_t)n, (uint64_t)b.ld, (uint32_t)(pair ? bn / 2 : bn), false, half));
     } else {
-        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
-        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, kTcBK, true));
+        FI_TRY(make_map(&maps[2], b.hi, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, (uint32_t)bk, true, half));
+        FI_TRY(make_map(&maps[3], b.lo, (uint64_t)n, (uint64_t)k, (uint64_t)b.ld, (uint32_t)bk, true, half));
     }
     ep.tma_split = 0;
-    if (ep.c_hi && !ep.transpose_out && out.ld_split % 4 == 0 && ((reinterpret_cast<uintptr_t>(ep.c_hi) | reinterpret_cast<uintptr_t>(ep.c_lo)) & 15) == 0 &&
-        !ep.c && !ep.mask) {
-        FI_TRY(make_map(&maps[4], ep.c_hi, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false));
-        FI_TRY(make_map(&maps[5], ep.c_lo, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false));
+    if (ep.c_hi && !ep.transpose_out && out.ld_split % (half ? 8 : 4) == 0 &&
+        ((reinterpret_cast<uintptr_t>(ep.c_hi) | reinterpret_cast<uintptr_t>(ep.c_lo)) & 15) == 0 && !ep.c && !ep.mask) {
+        // one store box per promotion warp: 32 rows x 128 bytes (32 fp32 or 64 fp16 columns)
+        FI_TRY(make_map(&maps[4], ep.c_hi, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false, half));
+        FI_TRY(make_map(&maps[5], ep.c_lo, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false, half));
         ep.tma_split = 1;
     } else {
         maps[4] = maps[0];
         maps[5] = maps[0];
         if (ep.colsum_out) return set_error(FI_ERR_ARG, "tcgen05 GEMM: fused column sums need the TMA split-output path");
+        if (half && ep.c_hi) return set_error(FI_ERR_ARG, "tcgen05 GEMM (fp16 format): the split output must be alone, dense and 16-byte aligned");
     }
     const int total = sh.num_m_blocks * sh.num_n_blocks * sh.num_splits;
     const int units = pair ? kNumSMs / 2 : kNumSMs;
     const int grid = (total < units ? total : units) * (pair ? 2 : 1);
     int rc;
-#define FI_TC(BNV, PAIRV)                                                                                    \
-    (trans == 0 ? launch_variant<BNV, false, false, PAIRV>(maps, sh, ep, grid, st)                           \
-                : trans == 1 ? launch_variant<BNV, false, true, PAIRV>(maps, sh, ep, grid, st)               \
-                             : launch_variant<BNV, true, true, PAIRV>(maps, sh, ep, grid, st))
-    if (bn == 128 && pair) rc = FI_TC(128, true);
-    else if (bn == 128) rc = FI_TC(128, false);
-    else if (bn == 64) rc = FI_TC(64, false);
-    else rc = FI_TC(32, false);
+#define FI_TC(BNV, PAIRV, HV)                                                                                \
+    (trans == 0 ? launch_variant<BNV, false, false, PAIRV, HV>(maps, sh, ep, grid, st)                       \
+                : trans == 1 ? launch_variant<BNV, false, true, PAIRV, HV>(maps, sh, ep, grid, st)           \
+                             : launch_variant<BNV, true, true, PAIRV, HV>(maps, sh, ep, grid, st))
+    if (half) {
+        if (bn == 128 && pair) rc = FI_TC(128, true, true);
+        else if (bn == 128) rc = FI_TC(128, false, true);
+        else rc = FI_TC(64, false, true);
+    } else if (bn == 128 && pair) rc = FI_TC(128, true, false);
+    else if (bn == 128) rc = FI_TC(128, false, false);
+    else if (bn == 64) rc = FI_TC(64, false, false);
+    else rc = FI_TC(32, false, false);
 #undef FI_TC
     FI_TRY(rc);
     if (sh.num_splits > 1) {
@@ -862,6 +1137,43 @@ int launch_gemm_tc(int trans, int m, int n, int k, const float* a, int lda, cons
     if (trans == 2 && ldc != n) {  // split-K partials need a dense output
         return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, nullptr, 0, st);
     }
+    return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, split_ws ? ws : nullptr, split_ws, st);
+}
+
+// ---- plain fp32 entry, 3xFP16 format: max |x| and split pre-passes for both operands, then the fp16 kernel --------
+static size_t pad8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+size_t gemm_h_workspace_bytes(int trans, int m, int n, int k) {
+    const size_t a_rows = trans == 2 ? k : m, a_cols = trans == 2 ? m : k;
+    const size_t b_rows = trans == 0 ? n : k, b_cols = trans == 0 ? k : n;
+    return 256 + 2 * align256(a_rows * pad8(a_cols) * 2) + 2 * align256(b_rows * pad8(b_cols) * 2) +
+           align256(gemm_tc_split_workspace_bytes(trans, m, n, k));
+}
+
+int launch_gemm_h(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc,
+                  const float* bias, int relu, const float* mask, int ldmask, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+    if (m <= 0 || n <= 0) return FI_OK;
+    if (workspace_bytes < gemm_h_workspace_bytes(trans, m, n, k) || !workspace)
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM (fp16 format): workspace too small (need %zu bytes)", gemm_h_workspace_bytes(trans, m, n, k));
+    const size_t a_rows = trans == 2 ? k : m, a_cols = trans == 2 ? m : k;
+    const size_t b_rows = trans == 0 ? n : k, b_cols = trans == 0 ? k : n;
+    const size_t a_ld = pad8(a_cols), b_ld = pad8(b_cols);
+    char* ws = static_cast<char*>(workspace);
+    HScale* hs = reinterpret_cast<HScale*>(ws); ws += 256;
+    void* a_hi = ws; ws += align256(a_rows * a_ld * 2);
+    void* a_lo = ws; ws += align256(a_rows * a_ld * 2);
+    void* b_hi = ws; ws += align256(b_rows * b_ld * 2);
+    void* b_lo = ws; ws += align256(b_rows * b_ld * 2);
+    FI_CUDA_OK(cudaMemsetAsync(hs, 0, 2 * sizeof(HScale), st));
+    FI_TRY(launch_amax(a, lda, a_rows, (int)a_cols, hs + 0, st));
+    FI_TRY(launch_amax(b, ldb, b_rows, (int)b_cols, hs + 1, st));
+    FI_TRY(launch_split_h(a, lda, a_rows, (int)a_cols, (int)a_ld, a_hi, a_lo, hs + 0, 1, st));
+    FI_TRY(launch_split_h(b, ldb, b_rows, (int)b_cols, (int)b_ld, b_hi, b_lo, hs + 1, 1, st));
+    SplitMat sa{a_hi, a_lo, (int)a_ld, hs + 0}, sb{b_hi, b_lo, (int)b_ld, hs + 1};
+    TcOut out{c, ldc, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
+    const size_t split_ws = gemm_tc_split_workspace_bytes(trans, m, n, k);
+    if (trans == 2 && ldc != n) return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, nullptr, 0, st);
     return launch_gemm_tc_split(trans, m, n, k, sa, sb, out, bias, relu, mask, ldmask, split_ws ? ws : nullptr, split_ws, st);
 }
 

@@ -421,10 +421,15 @@ int fi_learner_apply_update(fi_learner* l, int player) {
     if (l->dp_world > 1) {  // sum-allreduce of the flat gradient arena over NVLink
         if (!p->nccl_comm) return set_error(FI_ERR_STATE, "data parallelism configured but the communicator is missing");
         NcclApi& n = nccl();
+        // timed as "nccl_allreduce_grads" (bus bytes of a ring all-reduce: 2(N-1)/N x the arena); it also absorbs the wait
+        // for the slowest rank, so it reads as skew + transfer
+        fi::LaunchScope ls("nccl_allreduce_grads", p->stream,
+                           2.0 * (l->dp_world - 1) / l->dp_world * 4.0 * (double)l->param_count, fi::kWorkBytes);
         FI_NCCL_OK(n.GroupStart());
         FI_NCCL_OK(n.AllReduce(p->grads, p->grads, l->param_count, ncclFloat, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
         FI_NCCL_OK(n.AllReduce(p->d_losses, p->d_losses, 4, ncclDouble, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
         FI_NCCL_OK(n.GroupEnd());
+        ls.done_external();
     }
     p->opt_step++;
     FI_TRY(fi::launch_opt(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m,
@@ -760,6 +765,11 @@ __global__ void relu_mask_kernel(const float* __restrict__ a, const float* __res
         out[i] = (a[i] > 0.f || (lo && lo[i] > 0.f)) ? 1 : 0;
 }
 
+__global__ void relu_bits_expand_kernel(const uint32_t* __restrict__ bits, size_t n, unsigned char* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (bits[i >> 5] >> (i & 31)) & 1u;   // rows of 512 columns = 16 words: element i lives in word i / 32
+}
+
 int fi_learner_debug_relu_masks(fi_learner* l, int player, unsigned char* host, size_t n) {
     Player* p = get_player(l, player);
     if (!p || !host) return set_error(FI_ERR_ARG, "fi_learner_debug_relu_masks: null argument");
@@ -774,6 +784,13 @@ int fi_learner_debug_relu_masks(fi_learner* l, int player, unsigned char* host, 
     FI_CUDA_OK(cudaMalloc((void**)&dev, n));
     int rc = FI_OK;
     for (int layer = 0; layer < 5 && rc == FI_OK; layer++) {
+        if (const uint32_t* bits = farmer ? nullptr : fi::ac_relu_bits(p, layer)) {
+            // the tensor-core path keeps the decisions its backward pass used as bit masks
+            fi::LaunchScope ls("relu_bits_expand_kernel", p->stream, 1.125 * per_layer, fi::kWorkBytes);
+            relu_bits_expand_kernel<<<fi::kNumSMs * 4, 256, 0, p->stream>>>(bits, per_layer, dev + layer * per_layer);
+            rc = ls.done();
+            continue;
+        }
         const float *a = nullptr, *lo = nullptr;
         rc = farmer ? fi::farmer_activation(p, layer, &a, &lo) : fi::ac_activation(p, layer, &a, &lo);
         if (rc != FI_OK) break;

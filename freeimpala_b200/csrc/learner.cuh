@@ -109,6 +109,7 @@ int ac_infer_alloc(fi_learner* l, Player* p, size_t rows);
 int ac_infer(fi_learner* l, Player* p, const float* params, const float* obs_dev, size_t rows, float* out_dev,
              cudaStream_t stream);
 // ReLU outputs of hidden layer `layer` of the last forward: *a (+ *lo when stored as a hi/lo pair)
+const uint32_t* ac_relu_bits(Player* p, int layer);
 int ac_activation(Player* p, int layer, const float** a, const float** lo);
 int farmer_activation(Player* p, int layer, const float** a, const float** lo);
 // model_farmer.cu

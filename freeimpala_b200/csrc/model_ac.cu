@@ -14,18 +14,27 @@
 
 namespace fi {
 
-constexpr int kObsLd = 164;     // 162 observation words padded to a 16-byte multiple (TMA row stride)
-constexpr int kDheadLd = 32;    // 17 head gradients padded to one k-block
+constexpr int kObsLd = 164;     // 162 observation words padded to a 16-byte multiple (TMA row stride), 3xTF32 format
+constexpr int kObsLdH = 168;    // the same for fp16 elements
+constexpr int kDheadLd = 32;    // 17 head gradients padded to one TF32 k-block
+
+// HScale slots of the 3xFP16 format (one per split tensor)
+enum { kHsW = 0, kHsObs = 1, kHsDhead = 2, kHsAct0 = 3, kHsD0 = 8, kHsCount = 14 };
 
 struct AcTc {  // tensor-core path state, owned by the Player (Player::ac_tc)
-    float *w_hi = nullptr, *w_lo = nullptr;        // split parameter arena (same offsets as params)
-    float *w1_hi = nullptr, *w1_lo = nullptr;      // dense1.w re-laid out as [512, 164]
-    float *obs_hi = nullptr, *obs_lo = nullptr;    // [rows, 164]
-    float* act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* d_hi[2] = {nullptr, nullptr};
-    float* d_lo[2] = {nullptr, nullptr};
-    float *dhead_hi = nullptr, *dhead_lo = nullptr;  // [rows, 32], columns 17..31 stay zero
+    bool half = false;                             // 3xFP16 (fp16 pairs + per-tensor scales) instead of 3xTF32
+    size_t esz = 4;                                // bytes per element of the hi / lo arrays
+    int obs_ld = kObsLd;
+    HScale* hs = nullptr;                          // [kHsCount], fp16 format only
+    void *w_hi = nullptr, *w_lo = nullptr;         // split parameter arena (same element offsets as params)
+    void *w1_hi = nullptr, *w1_lo = nullptr;       // dense1.w re-laid out as [512, obs_ld]
+    void *obs_hi = nullptr, *obs_lo = nullptr;     // [rows, obs_ld]
+    void* act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* d_hi[2] = {nullptr, nullptr};
+    void* d_lo[2] = {nullptr, nullptr};
+    void *dhead_hi = nullptr, *dhead_lo = nullptr;   // [rows, 32], columns 17..31 stay zero
+    float* dhead = nullptr;                          // fp16 format: the loss head's plain fp32 output [rows, 17]
     uint32_t* relu_bits[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [rows, 16] words: act_l > 0, bit-packed
     float* colsum_part = nullptr;                    // [4 * ceil(rows/128), 512]: per-warp column sums from the dgrad epilogue
     void* ws = nullptr; size_t ws_bytes = 0;         // split-K partials
@@ -35,7 +44,7 @@ static bool use_tc(const fi_learner* l) { return l->cfg.gemm_mode != FI_GEMM_SIM
 
 int ac_alloc(fi_learner* l, Player* p) {
     const size_t rows = l->cfg.batch_size * l->cfg.entry_size;
-    if (l->cfg.gemm_mode == FI_GEMM_TCGEN05 && !gemm_tc_available())
+    if ((l->cfg.gemm_mode == FI_GEMM_TCGEN05 || l->cfg.gemm_mode == FI_GEMM_TCGEN05_F16) && !gemm_tc_available())
         return set_error(FI_ERR_STATE, "gemm_mode tcgen05 requested but cuTensorMapEncodeTiled is unavailable");
     FI_CUDA_OK(cudaMalloc((void**)&p->head, rows * kHead * sizeof(float)));
     p->colsum_ws_bytes = colsum_workspace_bytes((int)rows, kHid);
@@ -43,13 +52,23 @@ int ac_alloc(fi_learner* l, Player* p) {
     if (use_tc(l)) {
         AcTc* t = new AcTc();
         p->ac_tc = t;
-        const size_t ab = l->arena_elems * sizeof(float), rb = rows * kHid * sizeof(float);
+        // AUTO picks the 3xFP16 format (twice the tensor-core rate of 3xTF32 at the same 22 significant bits);
+        // FI_AC_FORMAT=tf32 keeps AUTO on 3xTF32 (A/B experiments)
+        const char* fmt = getenv("FI_AC_FORMAT");
+        t->half = l->cfg.gemm_mode == FI_GEMM_TCGEN05_F16 || (l->cfg.gemm_mode == FI_GEMM_AUTO && !(fmt && fmt[0] == 't'));
+        t->esz = t->half ? 2 : 4;
+        t->obs_ld = t->half ? kObsLdH : kObsLd;
+        const size_t ab = ((l->arena_elems + 7) & ~(size_t)7) * t->esz, rb = rows * kHid * t->esz;
         FI_CUDA_OK(cudaMalloc((void**)&t->w_hi, ab));
         FI_CUDA_OK(cudaMalloc((void**)&t->w_lo, ab));
-        FI_CUDA_OK(cudaMalloc((void**)&t->w1_hi, (size_t)kHid * kObsLd * sizeof(float)));
-        FI_CUDA_OK(cudaMalloc((void**)&t->w1_lo, (size_t)kHid * kObsLd * sizeof(float)));
-        FI_CUDA_OK(cudaMalloc((void**)&t->obs_hi, rows * kObsLd * sizeof(float)));
-        FI_CUDA_OK(cudaMalloc((void**)&t->obs_lo, rows * kObsLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_hi, (size_t)kHid * t->obs_ld * t->esz));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_lo, (size_t)kHid * t->obs_ld * t->esz));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_hi, rows * t->obs_ld * t->esz));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_lo, rows * t->obs_ld * t->esz));
+        if (t->half) {
+            FI_CUDA_OK(cudaMalloc((void**)&t->hs, kHsCount * sizeof(HScale)));
+            FI_CUDA_OK(cudaMalloc((void**)&t->dhead, rows * kHead * sizeof(float)));
+        }
         for (int i = 0; i < 5; i++) {
             FI_CUDA_OK(cudaMalloc((void**)&t->act_hi[i], rb));
             FI_CUDA_OK(cudaMalloc((void**)&t->act_lo[i], rb));
@@ -59,10 +78,10 @@ int ac_alloc(fi_learner* l, Player* p) {
             FI_CUDA_OK(cudaMalloc((void**)&t->d_hi[i], rb));
             FI_CUDA_OK(cudaMalloc((void**)&t->d_lo[i], rb));
         }
-        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_hi, rows * kDheadLd * sizeof(float)));
-        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_lo, rows * kDheadLd * sizeof(float)));
-        FI_CUDA_OK(cudaMemset(t->dhead_hi, 0, rows * kDheadLd * sizeof(float)));
-        FI_CUDA_OK(cudaMemset(t->dhead_lo, 0, rows * kDheadLd * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_hi, rows * kDheadLd * t->esz));
+        FI_CUDA_OK(cudaMalloc((void**)&t->dhead_lo, rows * kDheadLd * t->esz));
+        FI_CUDA_OK(cudaMemset(t->dhead_hi, 0, rows * kDheadLd * t->esz));
+        FI_CUDA_OK(cudaMemset(t->dhead_lo, 0, rows * kDheadLd * t->esz));
         FI_CUDA_OK(cudaMalloc((void**)&t->colsum_part, 4 * ((rows + 127) / 128) * kHid * sizeof(float)));
         size_t ws = 0;
         auto upd = [&](size_t b) { if (b > ws) ws = b; };
@@ -89,9 +108,9 @@ void ac_free(Player* p) {
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.clear();
     if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
-        float* f[] = {t->colsum_part, t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
-                      t->d_hi[1], t->d_lo[0], t->d_lo[1]};
-        for (float* x : f) if (x) cudaFree(x);
+        void* f[] = {t->colsum_part, t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
+                     t->d_hi[1], t->d_lo[0], t->d_lo[1], t->hs, t->dhead};
+        for (void* x : f) if (x) cudaFree(x);
         for (int i = 0; i < 5; i++) {
             if (t->act_hi[i]) cudaFree(t->act_hi[i]);
             if (t->act_lo[i]) cudaFree(t->act_lo[i]);
@@ -103,11 +122,18 @@ void ac_free(Player* p) {
     }
 }
 
+// Bit-packed ReLU decisions of hidden layer `layer` ([rows, 16] words) when the tensor-core path recorded them, else null.
+const uint32_t* ac_relu_bits(Player* p, int layer) {
+    AcTc* t = static_cast<AcTc*>(p->ac_tc);
+    return (t && layer >= 0 && layer < 5) ? t->relu_bits[layer] : nullptr;
+}
+
 int ac_activation(Player* p, int layer, const float** a, const float** lo) {
     if (layer < 0 || layer >= 5) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
     if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
-        *a = t->act_hi[layer];
-        *lo = t->act_lo[layer];
+        if (t->half) return set_error(FI_ERR_STATE, "activations are fp16 pairs in this format: use the bit masks");
+        *a = static_cast<const float*>(t->act_hi[layer]);
+        *lo = static_cast<const float*>(t->act_lo[layer]);
     } else {
         *a = p->act[layer];
         *lo = nullptr;
@@ -174,38 +200,64 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     cudaStream_t st = p->stream;
     float* g = p->grads;
     // pre-passes: weights (4.6 MB) and observations -> hi/lo pairs
-    FI_TRY(launch_split_tf32(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, (int)l->arena_elems, tc->w_hi, tc->w_lo, st));
-    FI_TRY(launch_split_tf32(p->params + T[0].offset, kZDim, kHid, kZDim, kObsLd, tc->w1_hi, tc->w1_lo, st));
-    FI_TRY(launch_split_tf32(batch, kRecWords, (size_t)rows, kZDim, kObsLd, tc->obs_hi, tc->obs_lo, st));
-    auto W = [&](int tensor, int ld) { return SplitMat{tc->w_hi + T[tensor].offset, tc->w_lo + T[tensor].offset, ld}; };
-    auto ACT = [&](int layer) { return SplitMat{tc->act_hi[layer], tc->act_lo[layer], kHid}; };
-    const SplitMat obs{tc->obs_hi, tc->obs_lo, kObsLd}, w1{tc->w1_hi, tc->w1_lo, kObsLd};
+    const bool H = tc->half;
+    HScale* hs = tc->hs;
+    auto HS = [&](int slot) -> HScale* { return H ? hs + slot : nullptr; };
+    auto off = [&](void* base, size_t elems) -> void* { return static_cast<char*>(base) + elems * tc->esz; };
+    if (H) {
+        // one scale for the whole parameter arena (weights and biases), one for the observations; every activation and
+        // back-propagated gradient gets its scale from the producing GEMM (bound k * amax_a * amax_b, gemm_tc.cu)
+        FI_CUDA_OK(cudaMemsetAsync(hs, 0, kHsCount * sizeof(HScale), st));
+        FI_TRY(launch_amax(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, hs + kHsW, st));
+        FI_TRY(launch_amax(batch, kRecWords, (size_t)rows, kZDim, hs + kHsObs, st));
+        const int arena_ld = (int)((l->arena_elems + 7) & ~(size_t)7);
+        FI_TRY(launch_split_h(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, arena_ld, tc->w_hi, tc->w_lo, hs + kHsW, 1, st));
+        FI_TRY(launch_split_h(p->params + T[0].offset, kZDim, kHid, kZDim, tc->obs_ld, tc->w1_hi, tc->w1_lo, hs + kHsW, 0, st));
+        FI_TRY(launch_split_h(batch, kRecWords, (size_t)rows, kZDim, tc->obs_ld, tc->obs_hi, tc->obs_lo, hs + kHsObs, 1, st));
+    } else {
+        FI_TRY(launch_split_tf32(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, (int)l->arena_elems, (float*)tc->w_hi, (float*)tc->w_lo, st));
+        FI_TRY(launch_split_tf32(p->params + T[0].offset, kZDim, kHid, kZDim, kObsLd, (float*)tc->w1_hi, (float*)tc->w1_lo, st));
+        FI_TRY(launch_split_tf32(batch, kRecWords, (size_t)rows, kZDim, kObsLd, (float*)tc->obs_hi, (float*)tc->obs_lo, st));
+    }
+    auto W = [&](int tensor, int ld) { return SplitMat{off(tc->w_hi, T[tensor].offset), off(tc->w_lo, T[tensor].offset), ld, HS(kHsW)}; };
+    auto ACT = [&](int layer) { return SplitMat{tc->act_hi[layer], tc->act_lo[layer], kHid, HS(kHsAct0 + layer)}; };
+    const SplitMat obs{tc->obs_hi, tc->obs_lo, tc->obs_ld, HS(kHsObs)}, w1{tc->w1_hi, tc->w1_lo, tc->obs_ld, HS(kHsW)};
     // forward: x_l = relu(x_{l-1} W_l^T + b_l), written as hi/lo pairs by the GEMM epilogue
     for (int layer = 0; layer < 5; layer++) {
         const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
         const SplitMat w = layer == 0 ? w1 : W(2 * layer, kHid);
-        const TcOut out{nullptr, 0, tc->act_hi[layer], tc->act_lo[layer], kHid, 0, nullptr, tc->relu_bits[layer], kHid / 32, nullptr};
+        const TcOut out{nullptr, 0, tc->act_hi[layer], tc->act_lo[layer], kHid, 0, nullptr, tc->relu_bits[layer], kHid / 32, nullptr,
+                        HS(kHsAct0 + layer), HS(kHsW)};
         FI_TRY(launch_gemm_tc_split(0, rows, kHid, layer == 0 ? kZDim : kHid, x, w, out, p->params + T[2 * layer + 1].offset, 1,
                                     nullptr, 0, nullptr, 0, st));
     }
     FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
                                 p->params + T[11].offset, 0, nullptr, 0, nullptr, 0, st));
     FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
-    FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
-                                   c.baseline_cost, c.entropy_cost, nullptr, nullptr, nullptr, p->d_losses, st, tc->dhead_hi,
-                                   tc->dhead_lo, kDheadLd));
-    const SplitMat dhead{tc->dhead_hi, tc->dhead_lo, kDheadLd};
+    if (H) {  // the loss head writes plain fp32 rows; max |x| and the fp16 split follow (13 MB)
+        FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
+                                       c.baseline_cost, c.entropy_cost, tc->dhead, nullptr, nullptr, p->d_losses, st));
+        FI_TRY(launch_amax(tc->dhead, kHead, (size_t)rows, kHead, hs + kHsDhead, st));
+        FI_TRY(launch_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, 1, st));
+    } else {
+        FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
+                                       c.baseline_cost, c.entropy_cost, nullptr, nullptr, nullptr, p->d_losses, st, (float*)tc->dhead_hi,
+                                       (float*)tc->dhead_lo, kDheadLd));
+    }
+    const SplitMat dhead{tc->dhead_hi, tc->dhead_lo, kDheadLd, HS(kHsDhead)};
     // head: db = colsum(dhead); dWh^T [512,17] = act4^T dhead, stored transposed as dWh [17,512];
     // d4 = (dhead Wh) * relu'(act4)
-    FI_TRY(launch_colsum2(tc->dhead_hi, tc->dhead_lo, kDheadLd, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
+    if (H) FI_TRY(launch_colsum(tc->dhead, kHead, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
+    else FI_TRY(launch_colsum2((float*)tc->dhead_hi, (float*)tc->dhead_lo, kDheadLd, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
     FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, TcOut{g + T[10].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, nullptr}, nullptr,
                                 0, nullptr, 0, tc->ws, tc->ws_bytes, st));
-    int cur = 0;
+    int cur = 0, dslot = kHsD0;
     FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHead, dhead, W(10, kHid),
-                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32, tc->colsum_part}, nullptr, 0,
-                                nullptr, 0, nullptr, 0, st));
+                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32, tc->colsum_part,
+                                      HS(dslot), nullptr},
+                                nullptr, 0, nullptr, 0, nullptr, 0, st));
     for (int layer = 4; layer >= 0; layer--) {
-        const SplitMat d{tc->d_hi[cur], tc->d_lo[cur], kHid};
+        const SplitMat d{tc->d_hi[cur], tc->d_lo[cur], kHid, HS(dslot)};
         const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
         const int k = layer == 0 ? kZDim : kHid;
         // bias gradient: the dgrad epilogue that produced d left per-32-row column sums (6.5 MB instead of re-reading 420 MB)
@@ -216,9 +268,10 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
         if (layer > 0) {
             FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHid, d, W(2 * layer, kHid),
                                         TcOut{nullptr, 0, tc->d_hi[cur ^ 1], tc->d_lo[cur ^ 1], kHid, 0, tc->relu_bits[layer - 1], nullptr,
-                                              kHid / 32, tc->colsum_part},
+                                              kHid / 32, tc->colsum_part, HS(dslot + 1), nullptr},
                                         nullptr, 0, nullptr, 0, nullptr, 0, st));
             cur ^= 1;
+            dslot++;
         }
     }
     return FI_OK;

@@ -139,9 +139,10 @@ typedef enum {
 } fi_loss_kind;
 typedef enum { FI_OPT_ADAM = 0, FI_OPT_SGD = 1, FI_OPT_ADAMW = 2 } fi_opt_kind; /* main.cpp:94-103 */
 typedef enum {
-    FI_GEMM_AUTO = 0,   /* tcgen05 3xTF32 where the shape allows, else SIMT fp32 */
+    FI_GEMM_AUTO = 0,   /* the fastest fp32-accurate tcgen05 path the shape allows, else SIMT fp32 */
     FI_GEMM_SIMT = 1,   /* fp32 FFMA kernels only */
-    FI_GEMM_TCGEN05 = 2 /* require the tcgen05 path (error if a shape cannot use it) */
+    FI_GEMM_TCGEN05 = 2, /* require the tcgen05 3xTF32 path (error if a shape cannot use it) */
+    FI_GEMM_TCGEN05_F16 = 3 /* require the tcgen05 3xFP16 path: fp16 hi/lo pairs with per-tensor power-of-two scales */
 } fi_gemm_mode;
 
 typedef struct fi_learner_config {

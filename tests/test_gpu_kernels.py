@@ -318,7 +318,7 @@ GEMM_CASES = [("NT", 640, 512, 162, 256), ("NT", 6400, 512, 512, 512), ("NT", 10
               ("NT", 300, 100, 70, 72), ("NN", 260, 40, 33, 36), ("TN", 130, 60, 77, 132)]
 
 
-@pytest.mark.parametrize("mode", ["simt", "tcgen05"])
+@pytest.mark.parametrize("mode", ["simt", "tcgen05", "tcgen05_f16"])
 @pytest.mark.parametrize("trans,m,n,k,lda", GEMM_CASES)
 def test_gemm_fp32_accuracy(fi, torch_cuda, trans, m, n, k, lda, mode):
     """C = op(A) op(B) (+bias, ReLU) within fp32 rounding of the float64 product: the learner's
@@ -352,3 +352,34 @@ def test_gemm_fp32_accuracy(fi, torch_cuda, trans, m, n, k, lda, mode):
     got = dC.cpu().numpy()
     scale = np.sqrt(k) * 1.0  # |sum of k products of N(0,1)| ~ sqrt(k)
     assert np.abs(got - ref).max() < 2e-6 * scale * 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trans", ["NT", "NN", "TN"])
+@pytest.mark.parametrize("sa,sb", [(1e-7, 3e4), (1e6, 1e-9), (1.0, 1.0)])
+def test_gemm_f16_format_dynamic_range(fi, torch_cuda, trans, sa, sb):
+    """3xFP16 format: per-tensor power-of-two scales keep fp32-level accuracy when the operands sit far from fp16's
+    range (gradients ~1e-7, large activations) and when a few outliers set the scale 1000x above the bulk."""
+    torch = torch_cuda
+    m, n, k = 384, 256, 700
+    rng = np.random.default_rng(5)
+    shape_a = (m, k) if trans != "TN" else (k, m)
+    shape_b = (n, k) if trans == "NT" else (k, n)
+    A = (rng.standard_normal(shape_a) * sa).astype(np.float32)
+    B = (rng.standard_normal(shape_b) * sb).astype(np.float32)
+    A.flat[::977] *= 1000.0   # outliers: the scale follows max |x|, the bulk sits 10 bits lower
+    B.flat[::1013] *= 1000.0
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    ref = A64 @ B64.T if trans == "NT" else (A64 @ B64 if trans == "NN" else A64.T @ B64)
+    absprod = np.abs(A64) @ np.abs(B64).T if trans == "NT" else (np.abs(A64) @ np.abs(B64) if trans == "NN" else np.abs(A64).T @ np.abs(B64))
+    dA, dB = _dev(torch, A), _dev(torch, B)
+    dC = torch.full((m, n), float("nan"), device="cuda")
+    ws_bytes = fi.ops.gemm_workspace_bytes(trans, m, n, k, "tcgen05_f16")
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device="cuda")
+    fi.ops.gemm(trans, m, n, k, dA.data_ptr(), shape_a[1], dB.data_ptr(), shape_b[1], dC.data_ptr(), n, None, False,
+                "tcgen05_f16", ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = dC.cpu().numpy().astype(np.float64)
+    # element-wise: within a few fp32 ulps of the sum of |products| (what an fp32 dot product guarantees)
+    assert np.all(np.abs(got - ref) <= 4e-6 * absprod / np.sqrt(k) * 8 + 1e-30), float(np.max(np.abs(got - ref) / (absprod + 1e-300)))
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-6

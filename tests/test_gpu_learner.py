@@ -23,7 +23,7 @@ def _ac_learner(fi, m, t, **kw):
     return fi.Learner(1, max(m, 2), t, m, 0, 0, kw.pop("ckpt", ""), "", 0, model="mlp_actor_critic", **kw)
 
 
-@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("gemm_mode", ["simt", "tcgen05", "tcgen05_f16", "auto"])
 @pytest.mark.parametrize("m,t,steps", [(4, 7, 3), (64, 100, 3), (9, 33, 2), (2, 1, 2), (1, 130, 1)])
 def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
     params = U.ac_params(11)
@@ -59,7 +59,7 @@ def test_actor_critic_vtrace_step_vs_oracle(fi, oracle, m, t, steps, gemm_mode):
     L.close()
 
 
-@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("gemm_mode", ["simt", "tcgen05", "tcgen05_f16"])
 def test_partial_batch_smaller_than_configured(fi, oracle, gemm_mode):
     """A batch of fewer trajectories than batch_size (the learner's buffers are sized for M) is a valid step."""
     m_cfg, m, t = 6, 3, 5
