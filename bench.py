@@ -19,6 +19,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import datetime
 import statistics
 import subprocess
 import sys
@@ -45,7 +46,8 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU per step (M)")
     ap.add_argument("--seq", type=int, default=100, help="transitions per trajectory (T = entry size S)")
-    ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--publish-every", type=int, default=1, help="publish the weights to the model store every N steps (reference: every step)")
+    ap.add_argument("--gemm-mode", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_f16"])
     ap.add_argument("--workload", default="vtrace", choices=["vtrace", "farmer"],
                     help="vtrace: MLP actor-critic V-trace step (headline); farmer: the reference's FarmerLstm/MSE/Adam step")
     ap.add_argument("--writers", type=int, default=0, help="actor threads feeding the ring in the e2e leg (0: min(16, host cores / ranks))")
@@ -73,12 +75,14 @@ def synth_slots(seed: int, m: int, t: int) -> np.ndarray:
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # nvidia-smi block-buffers its output when piped, so lines are dated by nvidia-smi's own `timestamp` field (wall clock,
+    # millisecond resolution), not by when they are read; the timed windows are wall-clock (time.time()) intervals
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device: int):
-        self.device, self.proc, self.lines = device, None, []
+    def __init__(self, devices):
+        self.devices, self.proc, self.lines = set(devices), None, []
 
     def start(self):
         try:
@@ -91,7 +95,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            self.lines.append(line.strip())
 
     def stop(self, windows):
         if not self.proc:
@@ -102,11 +106,17 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        self.thread.join(timeout=5)   # drain what nvidia-smi had buffered
         sm, mx, pw, reasons = [], [], [], set()
-        for ts, line in self.lines:
+        for line in self.lines:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9 or not f[0].isdigit() or int(f[0]) != self.device:
+            if len(f) < 10 or not f[1].isdigit() or int(f[1]) not in self.devices:
                 continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            f = f[1:]
             if not any(a <= ts <= b for a, b in windows):
                 continue
             try:
@@ -116,7 +126,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -222,6 +233,14 @@ def run_b200_arm(args):
         if world > 1:
             dist.barrier()
 
+    def all_ranks(x: float) -> list:
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -234,8 +253,9 @@ def run_b200_arm(args):
     K, W = args.steps, max(args.warmup, 0)
     cap = 2 * M
     farmer = args.workload == "farmer"
-    L = fi.Learner(1, cap, T, M, model="farmer_lstm" if farmer else "mlp_actor_critic", device=local,
-                   gemm_mode=args.gemm_mode, seed=1, lr=5e-4)
+    ring_cap = 4 * M   # learner's pinned-host/HBM ring: producers may run up to three batches ahead of the learner
+    L = fi.Learner(1, ring_cap, T, M, model="farmer_lstm" if farmer else "mlp_actor_critic", device=local,
+                   gemm_mode=args.gemm_mode, seed=1, lr=5e-4, publish_every=args.publish_every)
     from freeimpala_b200 import dp
     dp.init_learner_dp(L, rank, world)
     lib = fi.load_library()
@@ -258,7 +278,7 @@ def run_b200_arm(args):
         raw = FiBatch(batch_dev.data_ptr(), M, slot_bytes, stream_ptr, 0)
         L.trainModel(0, fi.Batch(raw))
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(range(world))   # rank 0 samples every GPU of the job: the slowest one sets the step time
     windows = []
     if rank == 0:
         sampler.start()
@@ -269,6 +289,8 @@ def run_b200_arm(args):
     L.sync(0)
     barrier()
     torch.cuda.synchronize()
+    per_rank_ms = []   # [pass][rank]: every rank's own device time per step (the headline is the max)
+
     def timed_pass(profiled: bool):
         L.sync(0)
         barrier()
@@ -277,7 +299,7 @@ def run_b200_arm(args):
         fi.prof_enable(profiled)
         n0 = fi.kernel_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
+        w0 = time.time()
         ev0.record(ext)
         for i in range(K):
             device_step(i)
@@ -285,9 +307,10 @@ def run_b200_arm(args):
         L.sync(0)
         torch.cuda.synchronize()
         barrier()
-        windows.append((w0, time.perf_counter()))
+        windows.append((w0, time.time()))
         fi.prof_enable(False)
-        return max_over_ranks(ev0.elapsed_time(ev1)), fi.kernel_launch_count() - n0, fi.prof_collect()
+        per_rank_ms.append(all_ranks(ev0.elapsed_time(ev1) / K))
+        return max(per_rank_ms[-1]) * K, fi.kernel_launch_count() - n0, fi.prof_collect()
 
     # Pass 1 is the headline: EXACTLY K steps, two events on the learner's stream, no instrumentation in between.
     # Pass 2 repeats the same K steps with every launch bracketed by its own event pair (fi_prof_enable) for the per-kernel
@@ -321,24 +344,37 @@ def run_b200_arm(args):
         def inplace_writer(j: int, steps: int, nw: int):
             # zero-copy producer (fi_ring_reserve_many / fi_ring_commit_many): the trajectory is produced IN the pinned slot
             # (what an MPI_Irecv posted into the slot does); here the slot keeps the synthetic trajectory written during
-            # warm-up and the producer stamps the step number into an unused word of its first record
-            burst = 32
+            # warm-up and the producer stamps the step number into an unused word of the first record of each burst
+            burst = 64
             for s in range(steps):
                 for i in range(j * burst, M, nw * burst):
                     n = min(burst, M - i)
                     ptrs, ticket = ring.reserve_many(n)
-                    for ptr in ptrs:
-                        C.c_uint32.from_address(ptr + 4 * 255).value = s
+                    C.c_uint32.from_address(ptrs[0] + 4 * 255).value = s
                     ring.commit_many(ticket, n)
+
+        e2e_losses = []
+        host_ms = {"readBatch": 0.0, "trainModel": 0.0}
 
         def e2e_steps(steps: int, writer, nw: int):
             ts = [threading.Thread(target=writer, args=(j, steps, nw)) for j in range(nw)]
             for t in ts:
                 t.start()
-            for _ in range(steps):
+            base = L.steps_done(0)
+            for s in range(steps):
+                t0 = time.perf_counter()
                 b = ring.readBatch(M, stream_ptr)
+                t1 = time.perf_counter()
                 L.trainModel(0, b)
-                L.last_losses(0)  # device -> host read of the step's result
+                t2 = time.perf_counter()
+                host_ms["readBatch"] += (t1 - t0) * 1e3
+                host_ms["trainModel"] += (t2 - t1) * 1e3
+                # device -> host read of a step's result, every step: the copy of step s is enqueued by trainModel; the host
+                # picks up step s-1's losses here (one step behind, as an asynchronous learner's logging is) so that the
+                # stream never drains between steps, and the last step's after the loop
+                if s > 0:
+                    e2e_losses.append(L.losses_at(0, base + s)[0])
+            e2e_losses.append(L.losses_at(0, base + steps)[0])
             for t in ts:
                 t.join()
 
@@ -346,24 +382,27 @@ def run_b200_arm(args):
             L.sync(0)
             barrier()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            t0, tw0 = time.perf_counter(), time.time()
             e2e_steps(K, writer, nw)
             L.sync(0)
             torch.cuda.synchronize()
-            t1 = time.perf_counter()
+            t1, tw1 = time.perf_counter(), time.time()
             barrier()
-            windows.append((t0, t1))
+            windows.append((tw0, tw1))
             return max_over_ranks(t1 - t0)
 
         e2e_steps(max(W, 4), copy_writer, nw_copy)   # warm-up; also leaves a valid trajectory in each of the 2M pinned slots
+        host_ms.update(readBatch=0.0, trainModel=0.0)
         zc_s = timed(inplace_writer, nw_zc)
+        zc_host = {k: v / K for k, v in host_ms.items()}   # rank 0's host time per step inside the two calls (blocking included)
         copy_s = timed(copy_writer, nw_copy)
         e2e = {"value": world * M * T * K / zc_s, "unit": UNIT, "ms_per_step": zc_s / K * 1e3,
                "h2d_bytes_per_step": world * M * slot_bytes,
                "d2h_bytes_per_step": world * (32 + 4 * L.param_count),
                "path": f"trajectories produced in place in the ring's pinned slots (fi_ring_reserve_many / fi_ring_commit_many, "
                        f"{nw_zc} producer threads) -> cudaMemcpyAsync per run of slots on the side stream -> readBatch (gather "
-                       f"kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H every step",
+                       f"kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H every step; the loss of step s is read by the host while step s+1 runs (fi_learner_losses_at)",
+               "losses_read": len(e2e_losses), "host_ms_per_step": zc_host,
                "write_copy": {"value": world * M * T * K / copy_s, "ms_per_step": copy_s / K * 1e3, "actor_threads": nw_copy,
                               "host_cores_per_rank": cores_per_rank,
                               "path": "same, but through SharedBuffer::write semantics (fi_ring_write_many): every trajectory is "
@@ -395,17 +434,22 @@ def run_b200_arm(args):
         d = kernels[dominant]
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
+        prof_name = "r1_gemm_f16x3" if "f16x3" in dominant else "r1_gemm_tc"
+        tpath = os.path.join(ROOT, "profiles", prof_name + "_traffic.json")
         if os.path.exists(tpath) and not farmer:
             tj = json.load(open(tpath))
             key = next((k for k in tj if k.startswith(dominant) and "BN=128" in k), None)
             if key:
-                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], f"profiles/r1_gemm_tc.md ({key}, big-layer launches)"
+                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], f"profiles/{prof_name}.md ({key}, big-layer launches)"
         roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
-                    "note": "tensor peak = cuBLAS bf16 sustained; this kernel computes fp32-accurate products "
-                            "(3xTF32 on tcgen05 or fp32 FFMA), whose ceiling is <= 1/6 of the bf16 peak"
-                            if d["bound"] == "tensor" else "HBM copy peak"}
+                    "note": ("tensor peak = cuBLAS bf16 sustained; `achieved` counts the 2mnk algorithmic flops, and every "
+                             "fp32-accurate product costs three tensor-core products (3xFP16: fp16 hi/lo pairs at the bf16 rate, "
+                             "ceiling 1/3 of the peak; 3xTF32: 1/6), so tensor-pipe work is 3 x achieved"
+                             if d["bound"] == "tensor" else "HBM copy peak")}
+        if d["bound"] == "tensor":
+            mult = 3.0 if "f16x3" in dominant else 6.0
+            roofline["frac_of_fp32_accurate_ceiling"] = d["frac"] * mult
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,12 +470,13 @@ def run_b200_arm(args):
                "config": {"workload": (f"farmer_lstm MSE/Adam learner step (the reference's train_step), batch {M} x T={T} per GPU"
                                        if farmer else f"vtrace_mlp_actor_critic learner step, batch {M} x T={T} per GPU "
                                                       f"(BASELINE.json configs[3]; records of 1024 B)"),
-                          "batch_per_gpu": M, "global_batch": M * world, "seq_len": T, "params": L.param_count,
+                          "batch_per_gpu": M, "global_batch": M * world, "ring_capacity_slots": ring_cap, "seq_len": T, "params": L.param_count,
                           "optimizer": "adam lr 5e-4", "gemm_mode": args.gemm_mode,
                           "parallelism": f"dp{world} (batch sharded, NCCL sum-allreduce of the flat gradient arena)",
                           "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
                           "flops_per_step": None if farmer else 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
-               "gpu_launches": int(launches), "ms_per_step_instrumented": ms_per_step_prof, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+               "gpu_launches": int(launches), "ms_per_step_instrumented": ms_per_step_prof,
+               "ms_per_step_by_rank": per_rank_ms[0], "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
                "cpu_baseline": cpu, "losses_last_step": [float(x) for x in losses]}
         print(json.dumps(out), flush=True)
     L.close()

@@ -75,6 +75,7 @@ SIGNATURES = {
     "fi_learner_stage_batch": (c_int, [_P, c_int, _P, c_size_t, C.POINTER(FiBatch)]),
     "fi_learner_last_losses": (c_int, [_P, c_int, C.POINTER(c_float)]),
     "fi_learner_last_losses_f64": (c_int, [_P, c_int, C.POINTER(c_double)]),
+    "fi_learner_losses_at": (c_int, [_P, c_int, c_u64, C.POINTER(c_float)]),
     "fi_learner_sync": (c_int, [_P, c_int]),
     "fi_learner_steps_done": (c_u64, [_P, c_int]),
     "fi_learner_debug_relu_masks": (c_int, [_P, c_int, _P, c_size_t]),

@@ -20,6 +20,16 @@ struct OptScalars {
     float lr, grad_scale;
 };
 
+// Optional by-products of the update, so that a learner step needs no copy-engine operation on its stream (copy-engine
+// hand-overs jitter by 10-300 us, and with 8 data-parallel ranks every step takes the worst rank's jitter):
+//  * snapshot: the updated parameters are also written here (the model store's device snapshot, +4 B/param);
+//  * losses_src/dst: block 0 copies the step's four loss sums into mapped pinned host memory (zero-copy read-back).
+struct OptExtras {
+    float* snapshot;
+    const double* losses_src;
+    double* losses_dst;
+};
+
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const OptScalars& s) {
     g *= s.grad_scale;
     p *= s.decay;
@@ -34,7 +44,12 @@ constexpr int kOptThreads = 256;
 template <bool kAdam>
 __global__ void __launch_bounds__(kOptThreads)
 fused_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                 float* __restrict__ v, size_t n, OptScalars s) {
+                 float* __restrict__ v, size_t n, OptScalars s, OptExtras x) {
+    if (x.losses_dst && blockIdx.x == 0 && threadIdx.x < 4) {
+        x.losses_dst[threadIdx.x] = x.losses_src[threadIdx.x];
+        __threadfence_system();
+    }
+    float4* s4 = reinterpret_cast<float4*>(x.snapshot);
     const size_t n4 = n / 4;
     const size_t stride = (size_t)gridDim.x * kOptThreads;
     float4* p4 = reinterpret_cast<float4*>(p);
@@ -59,6 +74,7 @@ fused_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
             pp.w -= s.lr * (gg.w * s.grad_scale);
         }
         p4[i] = pp;
+        if (s4) s4[i] = pp;
     }
     // tail (n % 4 values), handled by the first threads of block 0
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
@@ -73,18 +89,19 @@ fused_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
             pp -= s.lr * (g[i] * s.grad_scale);
         }
         p[i] = pp;
+        if (x.snapshot) x.snapshot[i] = pp;
     }
 }
 
 int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m,
-               float* v, float grad_scale, cudaStream_t stream) {
+               float* v, float grad_scale, cudaStream_t stream, float* snapshot, const double* losses_src, double* losses_dst) {
     if (n == 0) return FI_OK;
     if (!p || !g) return set_error(FI_ERR_ARG, "optimiser: null p/g");
     const bool adam = opt_kind == FI_OPT_ADAM || opt_kind == FI_OPT_ADAMW;
     if (!adam && opt_kind != FI_OPT_SGD) return set_error(FI_ERR_ARG, "optimiser: unknown kind %d", opt_kind);
     if (adam && (!m || !v)) return set_error(FI_ERR_ARG, "optimiser: Adam needs m and v");
     if (adam && step < 1) return set_error(FI_ERR_ARG, "optimiser: step counts from 1");
-    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15)
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)snapshot) & 15)
         return set_error(FI_ERR_ARG, "optimiser: arenas must be 16-byte aligned");
     const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
     const double wd = opt_kind == FI_OPT_ADAMW ? 1e-2 : 0.0;
@@ -103,9 +120,10 @@ int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const 
     const size_t cap = (size_t)kNumSMs * 8;  // whole waves of 8 resident CTAs per SM
     if (blocks > cap) blocks = cap;
     // algorithmic traffic: read p,g,m,v + write p,m,v = 28 B/param (SGD: 12 B/param)
-    LaunchScope ls("fused_opt_kernel", stream, (adam ? 28.0 : 12.0) * (double)n, kWorkBytes);
-    if (adam) fused_opt_kernel<true><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s);
-    else fused_opt_kernel<false><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s);
+    const OptExtras x{snapshot, losses_src, losses_src ? losses_dst : nullptr};
+    LaunchScope ls("fused_opt_kernel", stream, ((adam ? 28.0 : 12.0) + (snapshot ? 4.0 : 0.0)) * (double)n, kWorkBytes);
+    if (adam) fused_opt_kernel<true><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s, x);
+    else fused_opt_kernel<false><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s, x);
     return ls.done();
 }
 
@@ -113,5 +131,5 @@ int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const 
 
 extern "C" int fi_op_adam(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m,
                           float* v, float grad_scale, void* stream) {
-    return fi::launch_opt(opt_kind, lr, step, n, p, g, m, v, grad_scale, (cudaStream_t)stream);
+    return fi::launch_opt(opt_kind, lr, step, n, p, g, m, v, grad_scale, (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }

@@ -7,7 +7,8 @@ namespace fi {
 int launch_gather(const void* ring_base, size_t capacity, size_t slot_bytes, size_t first, size_t m, void* dst,
                   cudaStream_t stream);
 int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v,
-               float grad_scale, cudaStream_t stream);
+               float grad_scale, cudaStream_t stream, float* snapshot = nullptr, const double* losses_src = nullptr,
+               double* losses_dst = nullptr);
 int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount, const float* reward,
                        const float* value, const float* bootstrap, float rho_bar, float c_bar, float pg_rho_bar,
                        float lambda_, float* vs, float* pg_adv, cudaStream_t stream);
@@ -26,6 +27,8 @@ int launch_colsum(const float* x, int ldx, int m, int n, float* out, void* works
 int launch_colsum2(const float* x, const float* x2, int ldx, int m, int n, float* out, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream);
 size_t colsum_workspace_bytes(int m, int n);
+
+int launch_zero2(void* a, size_t a_bytes, void* b, size_t b_bytes, cudaStream_t stream);  // zero two small buffers, one kernel
 
 // out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).
 int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream);

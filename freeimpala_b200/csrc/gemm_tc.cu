@@ -233,7 +233,7 @@ __host__ __device__ __forceinline__ float hscale_from_bound(float bound) {
     int ex;
     frexpf(bound, &ex);                 // bound = f * 2^ex, f in [0.5, 1)
     int e = 14 - ex;
-    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    e = e > 60 ? 60 : (e < -60 ? -60 : e);   // products of two scales (and bias * scale_a * scale_b) stay finite
     return ldexpf(1.f, e);
 }
 // column sums of a 32 x 32 block held one row per lane (x[i] = column i of this lane's row) by recursive halving: after the
@@ -482,9 +482,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t leader_main_empty1 = PAIR ? map_to_cta(main_empty_bar(1), 0) : 0u;
         // fp16 format: corr carries lo' = 2048 lo; the accumulator is in units of scale_a * scale_b
         constexpr float kCorrMul = H ? (1.f / 2048.f) : 1.f;
-        float out_mul = 1.f, out_scale = 1.f;
+        float out_mul = 1.f, out_scale = 1.f, acc_unit = 1.f;
+        // TMA-split epilogues take the bias through the accumulator's initial value (loaded while the first chunk is
+        // still being computed) instead of 64 dependent loads per thread on the epilogue's critical path
+        const bool bias_in_acc = ep.bias != nullptr && ep.tma_split;
         if constexpr (H) {
             out_mul = ep.a_hs->inv * ep.b_hs->inv;
+            acc_unit = ep.a_hs->scale * ep.b_hs->scale;
             if (ep.out_hs) {
                 const float bound = (float)sh.k * ep.a_hs->amax * ep.b_hs->amax + (ep.bias_hs ? ep.bias_hs->amax : 0.f);
                 out_scale = hscale_from_bound(bound);
@@ -502,8 +506,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < sh.m;
             float acc[CW];
+            if (bias_in_acc) {
 #pragma unroll
-            for (int i = 0; i < CW; i++) acc[i] = 0.f;
+                for (int i = 0; i < CW; i++) acc[i] = (n0 + nc0 + i < sh.n) ? __ldg(ep.bias + n0 + nc0 + i) * acc_unit : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < CW; i++) acc[i] = 0.f;
+            }
             // bit-packed ReLU mask of this thread's row: one 16-byte load per tile, issued before the k-loop so that
             // its latency hides behind the MMAs (a float mask read in the epilogue was latency-bound: 4 warps per SM)
             uint32_t mw[CW / 32];
@@ -575,12 +584,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 uint32_t bits = 0;
 #pragma unroll
                                 for (int i = 0; i < 32; i++) {
-                                    float t = acc[c * 32 + i];
-                                    if (ep.bias && col0 + i < sh.n) t += __ldg(ep.bias + col0 + i);
+                                    float t = acc[c * 32 + i];   // bias arrived through the accumulator
                                     if (ep.relu) t = fmaxf(t, 0.f);
                                     bits |= (t > 0.f ? 1u : 0u) << i;
                                     acc[c * 32 + i] = t;
-                                    tmax_kernel = fmaxf(tmax_kernel, fabsf(t));
                                 }
                                 if (col0 < sh.n) {
                                     if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
@@ -590,25 +597,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     }
                                 }
                             }
+                            // both halves of the pair are converted in registers (in place of the accumulators) before the
+                            // staging tile is touched, so that the wait for the previous bulk store overlaps the arithmetic
+                            uint32_t wh[32], wl[32];
+                            __half2 hmax = __float2half2_rn(0.f);
+#pragma unroll
+                            for (int e = 0; e < 32; e++) {
+                                const float s0 = acc[2 * e] * out_scale, s1 = acc[2 * e + 1] * out_scale;
+                                const __half2 h = __floats2half2_rn(s0, s1);
+                                const float2 hf = __half22float2(h);
+                                // s - hf is exact in fp32; x 2048 folded into one fma
+                                const __half2 lo2 = __floats2half2_rn(fmaf(s0, 2048.f, -2048.f * hf.x), fmaf(s1, 2048.f, -2048.f * hf.y));
+                                hmax = __hmax2(hmax, __habs2(h));
+                                wh[e] = *reinterpret_cast<const uint32_t*>(&h);
+                                wl[e] = *reinterpret_cast<const uint32_t*>(&lo2);
+                            }
+                            // max |output| from the rounded hi parts (within 2^-11 of the exact value; consumers only use it in bounds)
+                            tmax_kernel = fmaxf(tmax_kernel, fmaxf(__low2float(hmax), __high2float(hmax)) * (1.001f / out_scale));
 #pragma unroll
                             for (int part = 0; part < 2; part++) {
                                 if (lane == 0) tma_store_wait_read();
                                 __syncwarp();
 #pragma unroll
                                 for (int j = 0; j < 8; j++) {   // 16-byte chunk j = columns 8j .. 8j+7
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) {
-                                        const float s0 = acc[8 * j + 2 * e] * out_scale, s1 = acc[8 * j + 2 * e + 1] * out_scale;
-                                        __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-                                        if (part == 1) {
-                                            h0 = __float2half_rn((s0 - __half2float(h0)) * 2048.f);
-                                            h1 = __float2half_rn((s1 - __half2float(h1)) * 2048.f);
-                                        }
-                                        w[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                    }
-                                    st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
-                                                  make_uint4(w[0], w[1], w[2], w[3]));  // 128B swizzle
+                                    const uint4 v = part == 0 ? make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3])
+                                                              : make_uint4(wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
+                                    st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);  // 128B swizzle
                                 }
                                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                                 __syncwarp();
@@ -638,8 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     uint32_t bits = 0;
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        float t = acc[c * 32 + i];
-                        if (ep.bias && col0 + i < sh.n) t += __ldg(ep.bias + col0 + i);
+                        float t = acc[c * 32 + i];   // bias arrived through the accumulator
                         if (ep.relu) t = fmaxf(t, 0.f);
                         bits |= (t > 0.f ? 1u : 0u) << i;
                         x[i] = t;
@@ -785,11 +798,17 @@ int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_o
 // ---- 3xFP16 pre-passes ---------------------------------------------------------------------------------------
 // max |x| over a [rows, cols] matrix (row stride ld_in) into hs->amax. Non-negative floats order like their bit patterns.
 __global__ void amax_kernel(const float* __restrict__ x, int ld_in, size_t rows, int cols, HScale* hs) {
-    const size_t total = rows * (size_t)cols;
     float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / cols;
-        m = fmaxf(m, fabsf(__ldg(x + r * ld_in + (i - r * cols))));
+    if (rows == 1) {  // flat vector (the parameter arena)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)cols; i += (size_t)gridDim.x * blockDim.x)
+            m = fmaxf(m, fabsf(__ldg(x + i)));
+    } else {          // one warp per row, lanes along the row: no per-element index arithmetic
+        const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        for (size_t r = warp; r < rows; r += nwarps) {
+            const float* xr = x + r * ld_in;
+            for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(__ldg(xr + c)));
+        }
     }
     const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
     if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&hs->amax), wm);
@@ -798,7 +817,7 @@ __global__ void amax_kernel(const float* __restrict__ x, int ld_in, size_t rows,
 int launch_amax(const float* x, int ld_in, size_t rows, int cols, HScale* hs, cudaStream_t st) {
     if (rows == 0 || cols == 0) return FI_OK;
     const size_t total = rows * (size_t)cols;
-    size_t blocks = (total + 1023) / 1024;
+    size_t blocks = rows == 1 ? (total + 1023) / 1024 : (rows + 7) / 8;
     if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
     LaunchScope ls("amax_kernel", st, 4.0 * (double)total, kWorkBytes);
     amax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, hs);
@@ -816,15 +835,29 @@ __global__ void split_h_kernel(const float* __restrict__ x, int ld_in, size_t ro
         hs->bound = hs->amax;
     }
     const int ldp = ld_out >> 1;
-    const size_t total = rows * (size_t)ldp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / ldp;
-        const int c = (int)(i - r * ldp) * 2;
-        const float v0 = c < cols ? __ldg(x + r * ld_in + c) * scale : 0.f;
-        const float v1 = c + 1 < cols ? __ldg(x + r * ld_in + c + 1) * scale : 0.f;
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        hi[i] = __halves2half2(h0, h1);
-        lo[i] = __halves2half2(__float2half_rn((v0 - __half2float(h0)) * 2048.f), __float2half_rn((v1 - __half2float(h1)) * 2048.f));
+    auto emit = [&](size_t o, float v0, float v1) {
+        v0 *= scale;
+        v1 *= scale;
+        const __half2 h = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(h);
+        hi[o] = h;
+        lo[o] = __floats2half2_rn(fmaf(v0, 2048.f, -2048.f * hf.x), fmaf(v1, 2048.f, -2048.f * hf.y));
+    };
+    if (rows == 1) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)ldp; i += (size_t)gridDim.x * blockDim.x) {
+            const int c = (int)i * 2;
+            emit(i, c < cols ? __ldg(x + c) : 0.f, c + 1 < cols ? __ldg(x + c + 1) : 0.f);
+        }
+        return;
+    }
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (size_t r = warp; r < rows; r += nwarps) {
+        const float* xr = x + r * ld_in;
+        for (int p = lane; p < ldp; p += 32) {
+            const int c = 2 * p;
+            emit(r * ldp + p, c < cols ? __ldg(xr + c) : 0.f, c + 1 < cols ? __ldg(xr + c + 1) : 0.f);
+        }
     }
 }
 
@@ -833,7 +866,7 @@ int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out,
     if (rows == 0 || ld_out == 0) return FI_OK;
     if (ld_out & 1) return set_error(FI_ERR_ARG, "split_h: ld_out must be even");
     const size_t total = rows * (size_t)(ld_out / 2);
-    size_t blocks = (total + 255) / 256;
+    size_t blocks = rows == 1 ? (total + 255) / 256 : (rows + 7) / 8;
     if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
     LaunchScope ls("split_h_kernel", st, 4.0 * (double)rows * cols + 4.0 * (double)rows * ld_out, kWorkBytes);
     split_h_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, ld_out, static_cast<__half2*>(hi), static_cast<__half2*>(lo), hs,
@@ -940,10 +973,12 @@ static int pair_policy() {
     }();
     return policy;
 }
-static bool use_pair(int trans, int m, int n) {
+// In the 3xFP16 format the MMAs take half as long per shared-memory byte delivered and the pair's cross-CTA hand-over
+// costs more than the halved B traffic returns (bench shape, TN: 121 us without pairs, 145 us with): pairs only on request.
+static bool use_pair(int trans, int m, int n, bool half) {
     const int policy = pair_policy();
-    if (policy == 0 || pick_bn(n) != 128 || m < 2 * kTcBM) return false;
-    return policy >= 2 || trans == 2;
+    if (policy == 0 || pick_bn(n, half) != 128 || m < 2 * kTcBM) return false;
+    return policy >= 2 || (trans == 2 && !half);
 }
 
 static int tc_splits(int trans, int m, int n, int k, bool pair, bool half = false) {
@@ -1012,7 +1047,7 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     const bool half = a.hs != nullptr;
     if (half != (b.hs != nullptr)) return set_error(FI_ERR_ARG, "tcgen05 GEMM: operands are in different split formats");
     const int bn = pick_bn(n, half), bk = half ? kTcBKh : kTcBK;
-    const bool pair = use_pair(trans, m, n);
+    const bool pair = use_pair(trans, m, n, half);
     TcShape sh;
     sh.m = m; sh.n = n; sh.k = k;
     sh.num_m_blocks = pair ? (m + 2 * kTcBM - 1) / (2 * kTcBM) : (m + kTcBM - 1) / kTcBM;

@@ -143,17 +143,26 @@ void CUDART_CB publish_cb(void* arg) {
     delete t;
 }
 
-// Enqueue the publication of the weights currently in p->params as `version`.
-int publish_async(Player* p, uint64_t version) {
+// Publication = (1) a device snapshot of the weights taken on the learner stream, (2) its D2H copy and the host-blob
+// flip on the publication stream. publish_begin makes the learner stream wait until the next snapshot slot is free and
+// returns it; the caller fills dev_snap[slot] on the learner stream (the fused optimiser writes it as a by-product, so the
+// step has no copy-engine operation; other callers copy) and calls publish_end.
+int publish_begin(Player* p, int* slot) {
     ModelStore& s = p->store;
     std::lock_guard<std::mutex> g(s.mu);
     const int sn = s.next_snap;
     if (s.snap_free_recorded[sn]) FI_CUDA_OK(cudaStreamWaitEvent(p->stream, s.snap_free[sn], 0));
     if (s.infer_recorded[sn]) FI_CUDA_OK(cudaStreamWaitEvent(p->stream, s.infer_done[sn], 0));
-    FI_CUDA_OK(cudaMemcpyAsync(s.dev_snap[sn], p->params, s.bytes, cudaMemcpyDeviceToDevice, p->stream));
+    *slot = sn;
+    return FI_OK;
+}
+
+int publish_end(Player* p, uint64_t version, int sn) {
+    ModelStore& s = p->store;
+    std::lock_guard<std::mutex> g(s.mu);
     FI_CUDA_OK(cudaEventRecord(s.snap_ready[sn], p->stream));
     s.newest_snap = sn;
-    s.next_snap = sn ^ 1;
+    s.next_snap = (sn + 1) % ModelStore::kSnaps;
     FI_CUDA_OK(cudaStreamWaitEvent(s.pub_stream, s.snap_ready[sn], 0));
     const int h = s.next_host;
     s.next_host = (h + 1) % 3;
@@ -167,6 +176,14 @@ int publish_async(Player* p, uint64_t version) {
         return set_error(FI_ERR_CUDA, "cudaLaunchHostFunc failed: %s", cudaGetErrorString(e));
     }
     return FI_OK;
+}
+
+// Enqueue the publication of the weights currently in p->params as `version` (snapshot by a device-to-device copy).
+int publish_async(Player* p, uint64_t version) {
+    int sn = 0;
+    FI_TRY(publish_begin(p, &sn));
+    FI_CUDA_OK(cudaMemcpyAsync(p->store.dev_snap[sn], p->params, p->store.bytes, cudaMemcpyDeviceToDevice, p->stream));
+    return publish_end(p, version, sn);
 }
 
 // Synchronous publication (create / set_params / load): everything idle on return.
@@ -194,8 +211,10 @@ void free_player(fi_learner* l, Player* p) {
     if (l->cfg.model == FI_MODEL_FARMER_LSTM) fi::farmer_free(p);
     else fi::ac_free(p);
     float* dev[] = {p->params, p->grads, p->adam_m, p->adam_v, p->d_a, p->d_b, p->head, p->dhead,
-                    p->inf_in, p->inf_x, p->inf_out, p->store.dev_snap[0], p->store.dev_snap[1]};
+                    p->inf_in, p->inf_x, p->inf_out};
     for (float* d : dev)
+        if (d) cudaFree(d);
+    for (float* d : p->store.dev_snap)
         if (d) cudaFree(d);
     void* devv[] = {p->d_losses, p->gemm_ws, p->colsum_ws, p->model_ws, p->stage_dev, p->inf_model_ws};
     for (void* d : devv)
@@ -204,10 +223,13 @@ void free_player(fi_learner* l, Player* p) {
                       p->store.host_buf[0], p->store.host_buf[1], p->store.host_buf[2]};
     for (void* h : pinned)
         if (h) cudaFreeHost(h);
-    cudaEvent_t evs[] = {p->losses_ready, p->batch_ready, p->store.snap_ready[0], p->store.snap_ready[1],
-                         p->store.snap_free[0], p->store.snap_free[1], p->store.infer_done[0], p->store.infer_done[1]};
-    for (cudaEvent_t e : evs)
-        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->loss_ev) if (e) cudaEventDestroy(e);
+    if (p->batch_ready) cudaEventDestroy(p->batch_ready);
+    for (int i = 0; i < ModelStore::kSnaps; i++) {
+        cudaEvent_t evs[] = {p->store.snap_ready[i], p->store.snap_free[i], p->store.infer_done[i]};
+        for (cudaEvent_t e : evs)
+            if (e) cudaEventDestroy(e);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->store.pub_stream) cudaStreamDestroy(p->store.pub_stream);
     if (p->infer_stream) cudaStreamDestroy(p->infer_stream);
@@ -229,13 +251,14 @@ int create_player(fi_learner* l, int index) {
     }
     FI_CUDA_OK(cudaMalloc((void**)&p->d_losses, 4 * sizeof(double)));
     FI_CUDA_OK(cudaMemset(p->d_losses, 0, 4 * sizeof(double)));
-    FI_CUDA_OK(cudaHostAlloc((void**)&p->h_losses, 4 * sizeof(double), cudaHostAllocPortable));
-    memset(p->h_losses, 0, 4 * sizeof(double));
-    FI_CUDA_OK(cudaEventCreateWithFlags(&p->losses_ready, cudaEventDisableTiming));
+    FI_CUDA_OK(cudaHostAlloc((void**)&p->h_losses, (Player::kLossRing + 1) * 4 * sizeof(double), cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(p->h_losses, 0, (Player::kLossRing + 1) * 4 * sizeof(double));
+    FI_CUDA_OK(cudaHostGetDevicePointer((void**)&p->h_losses_dev, p->h_losses, 0));
+    for (cudaEvent_t& e : p->loss_ev) FI_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     FI_CUDA_OK(cudaEventCreateWithFlags(&p->batch_ready, cudaEventDisableTiming));
     ModelStore& s = p->store;
     s.bytes = l->param_count * sizeof(float);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ModelStore::kSnaps; i++) {
         FI_CUDA_OK(cudaMalloc((void**)&s.dev_snap[i], abytes));
         FI_CUDA_OK(cudaEventCreateWithFlags(&s.snap_ready[i], cudaEventDisableTiming));
         FI_CUDA_OK(cudaEventCreateWithFlags(&s.snap_free[i], cudaEventDisableTiming));
@@ -432,13 +455,18 @@ int fi_learner_apply_update(fi_learner* l, int player) {
         ls.done_external();
     }
     p->opt_step++;
-    FI_TRY(fi::launch_opt(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m,
-                          p->adam_v, 1.0f, p->stream));
-    FI_CUDA_OK(cudaMemcpyAsync(p->h_losses, p->d_losses, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    FI_CUDA_OK(cudaEventRecord(p->losses_ready, p->stream));
     p->steps_done++;
     p->version++;  // generateRandomData(): version++ (data_structures.h:121-127), then updateModel
-    if (p->steps_done % (uint64_t)l->cfg.publish_every == 0) FI_TRY(publish_async(p, p->version));
+    const bool publish = p->steps_done % (uint64_t)l->cfg.publish_every == 0;
+    int sn = -1;
+    if (publish) FI_TRY(publish_begin(p, &sn));
+    // one kernel: the update, the model store's device snapshot and the loss read-back (into mapped pinned memory)
+    const int slot = (int)(p->steps_done % Player::kLossRing);
+    FI_TRY(fi::launch_opt(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m,
+                          p->adam_v, 1.0f, p->stream, publish ? p->store.dev_snap[sn] : nullptr, p->d_losses,
+                          p->h_losses_dev + 4 * slot));
+    FI_CUDA_OK(cudaEventRecord(p->loss_ev[slot], p->stream));
+    if (publish) FI_TRY(publish_end(p, p->version, sn));
     return FI_OK;
 }
 
@@ -451,21 +479,34 @@ int fi_learner_last_losses(fi_learner* l, int player, float losses[4]) {
     Player* p = get_player(l, player);
     if (!p || !losses) return set_error(FI_ERR_ARG, "fi_learner_last_losses: null argument");
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
+    const int slot = (int)(p->steps_done % Player::kLossRing);
     if (p->steps_done == 0 && p->grads_valid) {  // forward_backward only: read straight from the device
         FI_CUDA_OK(cudaMemcpyAsync(p->h_losses, p->d_losses, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-        FI_CUDA_OK(cudaEventRecord(p->losses_ready, p->stream));
+        FI_CUDA_OK(cudaEventRecord(p->loss_ev[0], p->stream));
     }
-    FI_CUDA_OK(cudaEventSynchronize(p->losses_ready));
-    for (int i = 0; i < 4; i++) losses[i] = (float)p->h_losses[i];
+    FI_CUDA_OK(cudaEventSynchronize(p->loss_ev[slot]));
+    for (int i = 0; i < 4; i++) losses[i] = (float)p->h_losses[4 * slot + i];
+    return FI_OK;
+}
+int fi_learner_losses_at(fi_learner* l, int player, uint64_t step, float losses[4]) {
+    Player* p = get_player(l, player);
+    if (!p || !losses) return set_error(FI_ERR_ARG, "fi_learner_losses_at: null argument");
+    if (step == 0 || step > p->steps_done || step + Player::kLossRing <= p->steps_done)
+        return set_error(FI_ERR_ARG, "fi_learner_losses_at: step %llu is not among the last %d of %llu", (unsigned long long)step,
+                         Player::kLossRing, (unsigned long long)p->steps_done);
+    FI_CUDA_OK(cudaSetDevice(l->cfg.device));
+    const int slot = (int)(step % Player::kLossRing);
+    FI_CUDA_OK(cudaEventSynchronize(p->loss_ev[slot]));
+    for (int i = 0; i < 4; i++) losses[i] = (float)p->h_losses[4 * slot + i];
     return FI_OK;
 }
 int fi_learner_last_losses_f64(fi_learner* l, int player, double losses[4]) {
     Player* p = get_player(l, player);
     if (!p || !losses) return set_error(FI_ERR_ARG, "fi_learner_last_losses_f64: null argument");
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
-    FI_CUDA_OK(cudaMemcpyAsync(p->h_losses, p->d_losses, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    FI_CUDA_OK(cudaMemcpyAsync(p->h_losses + 4 * Player::kLossRing, p->d_losses, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     FI_CUDA_OK(cudaStreamSynchronize(p->stream));
-    for (int i = 0; i < 4; i++) losses[i] = p->h_losses[i];
+    for (int i = 0; i < 4; i++) losses[i] = p->h_losses[4 * Player::kLossRing + i];  // scratch slot behind the ring
     return FI_OK;
 }
 uint64_t fi_learner_steps_done(fi_learner* l, int player) {

@@ -26,11 +26,17 @@ struct TensorSpec {
 // an exclusive mutex (the reference's getData() copies 1 MiB under model_mutex, :135-138).
 struct ModelStore {
     size_t bytes = 0;                       // blob size = param_count * 4
-    float* dev_snap[2] = {nullptr, nullptr};
-    cudaEvent_t snap_ready[2] = {nullptr, nullptr};  // D2D into the snapshot finished (learner stream)
-    cudaEvent_t snap_free[2] = {nullptr, nullptr};   // D2H out of the snapshot finished (pub stream)
-    cudaEvent_t infer_done[2] = {nullptr, nullptr};  // last inference reading the snapshot finished
-    bool snap_free_recorded[2] = {false, false}, infer_recorded[2] = {false, false};
+    // Device snapshots of the weights, taken by the learner stream and drained (D2H) by the publication stream. The
+    // publication stream also runs the host callback that flips the host blob, and a host callback runs when the OS
+    // schedules CUDA's callback thread: with 8 ranks on 16 cores that lags by milliseconds. The learner stream only
+    // ever waits for the snapshot it is about to overwrite, so kSnaps - 1 publications may be in flight before host
+    // latency reaches the learner (2 snapshots cost 24 % of the 8-GPU step: profiles/r1_scaling.md).
+    static constexpr int kSnaps = 8;
+    float* dev_snap[kSnaps] = {};
+    cudaEvent_t snap_ready[kSnaps] = {};  // D2D into the snapshot finished (learner stream)
+    cudaEvent_t snap_free[kSnaps] = {};   // D2H out of the snapshot finished (pub stream)
+    cudaEvent_t infer_done[kSnaps] = {};  // last inference reading the snapshot finished
+    bool snap_free_recorded[kSnaps] = {}, infer_recorded[kSnaps] = {};
     unsigned char* host_buf[3] = {nullptr, nullptr, nullptr};
     uint64_t buf_version[3] = {0, 0, 0};
     int published = 0;                      // index into host_buf, guarded by rw
@@ -59,8 +65,13 @@ struct Player {
     uint64_t steps_done = 0;
     uint64_t version = 1;       // version of the weights in `params` (Model ctor -> 1, :55-58,127)
     double* d_losses = nullptr; // device double[4]
-    double* h_losses = nullptr; // pinned double[4]
-    cudaEvent_t losses_ready = nullptr, batch_ready = nullptr;
+    // loss read-back ring: step s (1-based) lands in slot s % kLossRing of the pinned array, so that a host loop can read
+    // step s-1's losses while step s runs (fi_learner_losses_at) without stalling the stream
+    static constexpr int kLossRing = 8;
+    double* h_losses = nullptr; // pinned double[kLossRing + 1][4]
+    double* h_losses_dev = nullptr;  // the same memory as the device sees it (the optimiser kernel writes the losses there)
+    cudaEvent_t loss_ev[kLossRing] = {};
+    cudaEvent_t batch_ready = nullptr;
     size_t last_rows = 0;
     bool grads_valid = false;
     // step workspaces (model specific, sized for batch_size x entry_size rows)

@@ -164,7 +164,7 @@ static int ac_forward_backward_simt(fi_learner* l, Player* p, const float* batch
     const int rows = m * t;
     cudaStream_t st = p->stream;
     FI_TRY(ac_forward_simt(l, p->params, batch, kRecWords, rows, p->act.data(), p->head, p->gemm_ws, p->gemm_ws_bytes, st));
-    FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
+    FI_TRY(launch_zero2(p->d_losses, 4 * sizeof(double), nullptr, 0, st));
     FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                    c.baseline_cost, c.entropy_cost, p->dhead, nullptr, nullptr, p->d_losses, st));
     // head: dW = dhead^T act4, db = colsum(dhead), d4 = (dhead Wh) * relu'(act4)
@@ -207,7 +207,7 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     if (H) {
         // one scale for the whole parameter arena (weights and biases), one for the observations; every activation and
         // back-propagated gradient gets its scale from the producing GEMM (bound k * amax_a * amax_b, gemm_tc.cu)
-        FI_CUDA_OK(cudaMemsetAsync(hs, 0, kHsCount * sizeof(HScale), st));
+        FI_TRY(launch_zero2(hs, kHsCount * sizeof(HScale), p->d_losses, 4 * sizeof(double), st));
         FI_TRY(launch_amax(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, hs + kHsW, st));
         FI_TRY(launch_amax(batch, kRecWords, (size_t)rows, kZDim, hs + kHsObs, st));
         const int arena_ld = (int)((l->arena_elems + 7) & ~(size_t)7);
@@ -233,7 +233,7 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     }
     FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
                                 p->params + T[11].offset, 0, nullptr, 0, nullptr, 0, st));
-    FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
+    if (!H) FI_TRY(launch_zero2(p->d_losses, 4 * sizeof(double), nullptr, 0, st));
     if (H) {  // the loss head writes plain fp32 rows; max |x| and the fp16 split follow (13 MB)
         FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                        c.baseline_cost, c.entropy_cost, tc->dhead, nullptr, nullptr, p->d_losses, st));

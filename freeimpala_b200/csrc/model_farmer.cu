@@ -380,7 +380,7 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         FI_TRY(ls.done());
     }
     FI_TRY(farmer_forward(l, w, p->params, batch, kRecWords, m, t, st));
-    FI_CUDA_OK(cudaMemsetAsync(p->d_losses, 0, 4 * sizeof(double), st));
+    FI_TRY(launch_zero2(p->d_losses, 4 * sizeof(double), nullptr, 0, st));
     {
         LaunchScope ls("regression_loss_kernel", st, 12.0 * m, kWorkBytes);
         regression_loss_kernel<<<(m + 255) / 256, 256, 0, st>>>(w->y, w->target, m, l->cfg.loss, 1.0 / (double)global_m,

@@ -200,6 +200,12 @@ class Learner:
         check(self._lib.fi_learner_last_losses_f64(self._h, player_index, out), "fi_learner_last_losses_f64")
         return np.array(list(out))
 
+    def losses_at(self, player_index: int, step: int) -> np.ndarray:
+        """Losses of optimiser step `step` (1-based, one of the last 8): waits only for that step's read-back."""
+        out = (C.c_float * 4)()
+        check(self._lib.fi_learner_losses_at(self._h, player_index, step, out), "fi_learner_losses_at")
+        return np.array(list(out), dtype=np.float64)
+
     def debug_relu_masks(self, player_index: int, rows: int) -> np.ndarray:
         out = np.empty((5, rows * 512), np.uint8)
         check(self._lib.fi_learner_debug_relu_masks(self._h, player_index, out.ctypes.data, out.size),

@@ -193,6 +193,9 @@ FI_API int fi_learner_stage_batch(fi_learner* l, int player, const void* host, s
 FI_API int fi_learner_last_losses(fi_learner* l, int player, float losses[4]);
 /* Same numbers in the double precision they are accumulated in (synchronises the stream). */
 FI_API int fi_learner_last_losses_f64(fi_learner* l, int player, double losses[4]);
+/* Losses of optimiser step `step` (1-based count of fi_learner_step calls on this player); valid for the last 8 steps.
+ * Waits only for that step's read-back, so a host loop can log step s-1 while step s runs. */
+FI_API int fi_learner_losses_at(fi_learner* l, int player, uint64_t step, float losses[4]);
 /* Wait until everything enqueued for this player (step and weight publication) has finished. */
 FI_API int fi_learner_sync(fi_learner* l, int player);
 FI_API uint64_t fi_learner_steps_done(fi_learner* l, int player);

@@ -264,3 +264,21 @@ def test_farmer_step_through_ring_decodes_records(fi, oracle):
     want = O.loss_grad(z, x, tg)
     assert abs(L.last_losses(0)[0] - want) <= TOL * abs(want)
     L.close()
+
+
+def test_losses_at_reads_back_any_of_the_last_steps(fi):
+    """fi_learner_losses_at: per-step loss read-back ring (a host loop logs step s-1 while step s runs)."""
+    m, t = 3, 6
+    L = _ac_learner(fi, m, t, gemm_mode="simt")
+    seen = []
+    for s in range(11):
+        obs, mu, act, rew, disc, boot = U.vtrace_batch(300 + s, m, t)
+        L.trainModel(0, L.stage_batch(0, po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)))
+        seen.append(L.last_losses(0))
+    assert L.steps_done(0) == 11
+    for step in range(4, 12):   # the ring keeps the last 8 steps
+        np.testing.assert_allclose(L.losses_at(0, step), seen[step - 1], rtol=1e-6)
+    for bad in (0, 3, 12):
+        with pytest.raises(fi.FiError):
+            L.losses_at(0, bad)
+    L.close()

@@ -25,7 +25,9 @@ def page(rep, name):
 def label(kname):
     if "gemm_tc_kernel" in kname:
         a = kname.split("<")[1].split(">")[0].replace("(int)", "").replace("(bool)", "").replace(" ", "").split(",")
-        return f"gemm_tc_kernel<{'NT' if a[2] == '0' else ('NN' if a[1] == '0' else 'TN')}> BN={a[0]}"
+        fmt = "f16x3," if len(a) > 4 and a[4] == "1" else ""
+        pair = " pair" if len(a) > 3 and a[3] == "1" else ""
+        return f"gemm_tc_kernel<{fmt}{'NT' if a[2] == '0' else ('NN' if a[1] == '0' else 'TN')}> BN={a[0]}{pair}"
     return kname.split("(")[0].replace("void ", "").replace("fi::", "")
 
 
