@@ -499,6 +499,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
         }
+        float bias_next[CW / 32];
+#pragma unroll
+        for (int c = 0; c < CW / 32; c++) bias_next[c] = 0.f;
+        if (bias_in_acc && unit < total_work) {
+            const int fn0 = ((unit % tiles) % sh.num_n_blocks) * BN + nc0;
+#pragma unroll
+            for (int c = 0; c < CW / 32; c++) bias_next[c] = (fn0 + c * 32 + lane < sh.n) ? __ldg(ep.bias + fn0 + c * 32 + lane) : 0.f;
+        }
         for (int w = unit; w < total_work; w += num_units) {
             const int tile = w % tiles, split = w / tiles;
             const int m0 = (tile / sh.num_n_blocks) * kTileM + (int)cta_rank * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
@@ -507,8 +515,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const bool row_ok = row < sh.m;
             float acc[CW];
             if (bias_in_acc) {
+                // lane l holds the bias of columns l and 32 + l of this warp's range, fetched one tile ahead (below), and
+                // the initial accumulators are built with shuffles: no load latency at the start of a tile, where the
+                // MMAs of the next chunk are already waiting for the promotion warps
 #pragma unroll
-                for (int i = 0; i < CW; i++) acc[i] = (n0 + nc0 + i < sh.n) ? __ldg(ep.bias + n0 + nc0 + i) * acc_unit : 0.f;
+                for (int i = 0; i < CW; i++) acc[i] = __shfl_sync(0xFFFFFFFFu, i < 32 ? bias_next[0] : bias_next[CW > 32 ? 1 : 0], i & 31) * acc_unit;
+                const int wn = w + num_units;
+                if (wn < total_work) {
+                    const int nn0 = ((wn % tiles) % sh.num_n_blocks) * BN + nc0;
+#pragma unroll
+                    for (int c = 0; c < CW / 32; c++) bias_next[c] = (nn0 + c * 32 + lane < sh.n) ? __ldg(ep.bias + nn0 + c * 32 + lane) : 0.f;
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < CW; i++) acc[i] = 0.f;
@@ -597,39 +614,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     }
                                 }
                             }
-                            // both halves of the pair are converted in registers (in place of the accumulators) before the
-                            // staging tile is touched, so that the wait for the previous bulk store overlaps the arithmetic
-                            uint32_t wh[32], wl[32];
+                            // hi parts first: converted, staged and handed to the TMA; the lo' parts (the longer arithmetic) are
+                            // computed while that bulk store reads the staging tile, so the wait before reusing it is short
+                            uint32_t wh[32];
                             __half2 hmax = __float2half2_rn(0.f);
 #pragma unroll
                             for (int e = 0; e < 32; e++) {
-                                const float s0 = acc[2 * e] * out_scale, s1 = acc[2 * e + 1] * out_scale;
-                                const __half2 h = __floats2half2_rn(s0, s1);
-                                const float2 hf = __half22float2(h);
-                                // s - hf is exact in fp32; x 2048 folded into one fma
-                                const __half2 lo2 = __floats2half2_rn(fmaf(s0, 2048.f, -2048.f * hf.x), fmaf(s1, 2048.f, -2048.f * hf.y));
+                                acc[2 * e] *= out_scale;
+                                acc[2 * e + 1] *= out_scale;
+                                const __half2 h = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
                                 hmax = __hmax2(hmax, __habs2(h));
                                 wh[e] = *reinterpret_cast<const uint32_t*>(&h);
-                                wl[e] = *reinterpret_cast<const uint32_t*>(&lo2);
                             }
                             // max |output| from the rounded hi parts (within 2^-11 of the exact value; consumers only use it in bounds)
                             tmax_kernel = fmaxf(tmax_kernel, fmaxf(__low2float(hmax), __high2float(hmax)) * (1.001f / out_scale));
+                            if (lane == 0) tma_store_wait_read();   // the previous tile's lo' store: long finished
+                            __syncwarp();
 #pragma unroll
-                            for (int part = 0; part < 2; part++) {
-                                if (lane == 0) tma_store_wait_read();
-                                __syncwarp();
+                            for (int j = 0; j < 8; j++)   // 16-byte chunk j = columns 8j .. 8j+7, 128B swizzle
+                                st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
+                                              make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&map_c_hi, stage_tile, colw0, rbase);
+                                tma_store_commit();
+                            }
 #pragma unroll
-                                for (int j = 0; j < 8; j++) {   // 16-byte chunk j = columns 8j .. 8j+7
-                                    const uint4 v = part == 0 ? make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3])
-                                                              : make_uint4(wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
-                                    st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);  // 128B swizzle
-                                }
-                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                __syncwarp();
-                                if (lane == 0) {
-                                    tma_store_2d(part == 0 ? &map_c_hi : &map_c_lo, stage_tile, colw0, rbase);
-                                    tma_store_commit();
-                                }
+                            for (int e = 0; e < 32; e++) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&wh[e]));
+                                // s - hf is exact in fp32; x 2048 folded into one fma
+                                const __half2 lo2 = __floats2half2_rn(fmaf(acc[2 * e], 2048.f, -2048.f * hf.x), fmaf(acc[2 * e + 1], 2048.f, -2048.f * hf.y));
+                                wh[e] = *reinterpret_cast<const uint32_t*>(&lo2);
+                            }
+                            if (lane == 0) tma_store_wait_read();
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
+                                              make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&map_c_lo, stage_tile, colw0, rbase);
+                                tma_store_commit();
                             }
                         }
                     }
