@@ -282,3 +282,70 @@ def test_losses_at_reads_back_any_of_the_last_steps(fi):
         with pytest.raises(fi.FiError):
             L.losses_at(0, bad)
     L.close()
+
+
+def test_full_size_step_properties(fi):
+    """BASELINE.json's bench shape (1024 x 100), where the float64 oracle is too slow to be the checker:
+    (1) two independent implementations of the step — fp32 FFMA GEMMs and the tcgen05 3xFP16 path — agree on the
+        losses to 1e-5 and on the gradients to fp32 rounding (apart from the ReLU units within rounding of zero that the
+        two decide differently; the decisions themselves are compared);
+    (2) the losses are sums over trajectories, so the gradient of the full batch equals the sum of the gradients of its
+        two halves (every trajectory is processed identically whatever the batch around it: tile position, split-K
+        partition and the per-tensor fp16 scales all change with the batch)."""
+    m, t = 1024, 100
+    params = U.ac_params(5)
+    obs, mu, act, rew, disc, boot = U.vtrace_batch(77, m, t, done_p=0.02)
+    slots = po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)
+    A = _ac_learner(fi, m, t, gemm_mode="auto")
+    B = _ac_learner(fi, m, t, gemm_mode="simt")
+    res = {}
+    for name, L in (("tc", A), ("simt", B)):
+        L.set_params(0, params)
+        L.forward_backward(0, L.stage_batch(0, slots))
+        res[name] = (L.last_losses(0), L.get_grads(0), L.debug_relu_masks(0, m * t))
+    B.close()
+    (la, ga, ma), (lb, gb, mb) = res["tc"], res["simt"]
+    np.testing.assert_allclose(la, lb, rtol=1e-5, atol=1e-6 * abs(lb[0]))
+    flips = int(np.count_nonzero(ma != mb))
+    assert flips <= 4 + 2e-5 * ma.size / 5, flips       # same budget as the oracle comparison at small sizes
+    full_rel, trimmed = U.rel_l2(ga, gb), U.trimmed_rel_l2(ga, gb)
+    print(f"full-size cross-path: relu flips {flips}, grads rel_l2 {full_rel:.3e}, trimmed {trimmed:.3e}")
+    # a unit decided differently moves a whole weight-gradient row of every layer below it (both are valid subgradients at
+    # the kink), so across two implementations the gradients are only held to the flip-limited level; the tight gradient
+    # check at this size is (2), where both sides make the same decisions
+    assert trimmed < 1e-3 and full_rel < 2e-3
+    # (2) halves
+    g_sum, l_sum = np.zeros_like(ga, dtype=np.float64), np.zeros(4)
+    for half in (slots[: m // 2], slots[m // 2:]):
+        A.forward_backward(0, A.stage_batch(0, half))
+        g_sum += A.get_grads(0)
+        l_sum += A.last_losses(0)
+    np.testing.assert_allclose(l_sum, la, rtol=2e-6, atol=1e-6 * abs(la[0]))
+    half_rel = U.rel_l2(g_sum, ga)
+    print(f"full-size halves: grads rel_l2 {half_rel:.3e}")
+    assert half_rel < 1e-5
+    A.close()
+
+
+def test_full_size_step_vs_oracle(fi, oracle):
+    """One V-trace learner step at the bench shape (1024 x 100, default tensor-core path) against the float64 oracle
+    (tens of seconds of host time): losses, gradients and the parameters after the Adam update within 1e-5."""
+    m, t = 1024, 100
+    params = U.ac_params(6)
+    obs, mu, act, rew, disc, boot = U.vtrace_batch(78, m, t, done_p=0.02)
+    L = _ac_learner(fi, m, t)
+    L.set_params(0, params)
+    L.forward_backward(0, L.stage_batch(0, po.pack_vtrace_slots(obs, mu, act, rew, disc, boot)))
+    got, grads, masks = L.last_losses(0), L.get_grads(0), L.debug_relu_masks(0, m * t)
+    O = oracle.actor_critic(params, lr=5e-4)
+    want, n_over, max_over = O.loss_grad_masked(obs, mu, act, rew, disc, boot, masks)
+    assert n_over <= 4 + 2e-5 * masks.size and max_over < 1e-5, (n_over, max_over)
+    np.testing.assert_allclose(got, want, rtol=TOL, atol=1e-6 * abs(want[0]))
+    rel = U.rel_l2(grads, O.grads())
+    print(f"full-size vs oracle: overridden relu units {n_over} (max |pre-activation| {max_over:.2e}), grads rel_l2 {rel:.3e}")
+    assert rel < TOL
+    L.apply_update(0)
+    O.set_grads(np.asarray(grads, np.float64))     # teacher-forced Adam step (see _util.AdamParity)
+    O.opt_step()
+    assert U.rel_l2(L.get_params(0), O.params()) < TOL
+    L.close()
