@@ -29,6 +29,7 @@ int launch_colsum2(const float* x, const float* x2, int ldx, int m, int n, float
 size_t colsum_workspace_bytes(int m, int n);
 
 int launch_zero2(void* a, size_t a_bytes, void* b, size_t b_bytes, cudaStream_t stream);  // zero two small buffers, one kernel
+int launch_copy_words(float* dst, const float* src, int n, cudaStream_t stream);            // small device copy as a kernel
 
 // out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).
 int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream);

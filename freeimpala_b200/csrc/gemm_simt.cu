@@ -374,6 +374,15 @@ __global__ void zero_words_kernel(uint32_t* a, int na, uint32_t* b, int nb) {
     for (int i = threadIdx.x; i < na; i += blockDim.x) a[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) b[i] = 0u;
 }
+__global__ void copy_words_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int launch_copy_words(float* dst, const float* src, int n, cudaStream_t st) {
+    if (n <= 0) return FI_OK;
+    LaunchScope ls("copy_words_kernel", st, 8.0 * n, kWorkBytes);
+    copy_words_kernel<<<(n + 255) / 256 > 64 ? 64 : (n + 255) / 256, 256, 0, st>>>(dst, src, n);
+    return ls.done();
+}
 int launch_zero2(void* a, size_t a_bytes, void* b, size_t b_bytes, cudaStream_t st) {
     if ((a_bytes | b_bytes) & 3) return set_error(FI_ERR_ARG, "launch_zero2: sizes must be multiples of 4");
     LaunchScope ls("zero_words_kernel", st, (double)(a_bytes + b_bytes), kWorkBytes);

@@ -33,7 +33,19 @@ struct FarmerWs {
     void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;
     void* colsum_ws = nullptr; size_t colsum_ws_bytes = 0;
     size_t rows = 0, t = 0;
+    // tensor-core path of the three [rows*T]-sized products (input projection and the two LSTM weight gradients): 3xFP16
+    // operand pairs (gemm_tc.cu), each big operand split ONCE per step — the observations serve the projection and the
+    // W_ih gradient, the gate gradients serve both weight gradients
+    bool half = false;
+    HScale* hs = nullptr;                          // [4]: observations, W_ih, gate gradients, h_prev
+    void *obs_hi = nullptr, *obs_lo = nullptr;     // [rows*T, 168] fp16
+    void *wih_hi = nullptr, *wih_lo = nullptr;     // [512, 168]
+    void *dg_hi = nullptr, *dg_lo = nullptr;       // [rows*T, 512]
+    void *hp_hi = nullptr, *hp_lo = nullptr;       // [rows*T, 128]
+    void* split_ws = nullptr; size_t split_ws_bytes = 0;
 };
+constexpr int kObsLdH = 168;   // 162 observation words padded to a 16-byte multiple of fp16
+enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -278,6 +290,9 @@ static void ws_release(FarmerWs* w) {
         if (p) cudaFree(p);
     if (w->gemm_ws) cudaFree(w->gemm_ws);
     if (w->colsum_ws) cudaFree(w->colsum_ws);
+    void* h[] = {w->hs, w->obs_hi, w->obs_lo, w->wih_hi, w->wih_lo, w->dg_hi, w->dg_lo, w->hp_hi, w->hp_lo, w->split_ws};
+    for (void* p : h)
+        if (p) cudaFree(p);
     delete w;
 }
 
@@ -307,10 +322,35 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
         upd(gemm_workspace_bytes(mode, 2, kHid, kFeat, (int)rows));
         upd(gemm_workspace_bytes(mode, 2, kHid, kHid, (int)rows));
         upd(gemm_workspace_bytes(mode, 2, 1, kHid, (int)rows));
+        // forward (NT) and dgrad (NN) shapes: the 3xFP16 operand copies are laid out per operand shape
+        upd(gemm_workspace_bytes(mode, 0, (int)rt, kG4, kZDim));
+        upd(gemm_workspace_bytes(mode, 0, (int)rows, kHid, kFeat));
+        upd(gemm_workspace_bytes(mode, 0, (int)rows, kHid, kHid));
+        upd(gemm_workspace_bytes(mode, 0, (int)rows, 1, kHid));
+        upd(gemm_workspace_bytes(mode, 1, (int)rows, kHid, 1));
+        upd(gemm_workspace_bytes(mode, 1, (int)rows, kFeat, kHid));
+        upd(gemm_workspace_bytes(mode, 1, (int)rows, kHid, kHid));
         w->gemm_ws_bytes = ws;
         if (ws) FI_CUDA_OK(cudaMalloc(&w->gemm_ws, ws));
         w->colsum_ws_bytes = colsum_workspace_bytes((int)rt, kG4);
         FI_CUDA_OK(cudaMalloc(&w->colsum_ws, w->colsum_ws_bytes));
+        w->half = (mode == FI_GEMM_AUTO || mode == FI_GEMM_TCGEN05_F16) && gemm_tc_available();
+        if (w->half) {
+            FI_CUDA_OK(cudaMalloc((void**)&w->hs, 4 * sizeof(HScale)));
+            FI_CUDA_OK(cudaMalloc(&w->obs_hi, rt * kObsLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->obs_lo, rt * kObsLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->wih_hi, (size_t)kG4 * kObsLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->wih_lo, (size_t)kG4 * kObsLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->dg_hi, rt * kG4 * 2));
+            FI_CUDA_OK(cudaMalloc(&w->dg_lo, rt * kG4 * 2));
+            FI_CUDA_OK(cudaMalloc(&w->hp_hi, rt * kLstmH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->hp_lo, rt * kLstmH * 2));
+            size_t sw = gemm_tc_split_workspace_bytes(2, kG4, kZDim, (int)rt);
+            const size_t sw2 = gemm_tc_split_workspace_bytes(2, kG4, kLstmH, (int)rt);
+            if (sw2 > sw) sw = sw2;
+            w->split_ws_bytes = sw;
+            if (sw) FI_CUDA_OK(cudaMalloc(&w->split_ws, sw));
+        }
     }
     return FI_OK;
 }
@@ -329,11 +369,18 @@ void farmer_free(Player* p) {
     p->farmer_ws = p->farmer_inf_ws = nullptr;
 }
 
+// The tensor-core path pays four pre-pass launches per product: taken from ~64 MFLOP up (as launch_gemm's AUTO does), always
+// when the 3xFP16 mode is required.
+static bool farmer_use_half(const fi_learner* l, const FarmerWs* w, int rt) {
+    return w->half && (l->cfg.gemm_mode == FI_GEMM_TCGEN05_F16 || 2.0 * rt * kG4 * kZDim >= 64e6);
+}
+
 // z rows: (b,t) at z + (b*t + s) * ldz. Leaves y[m], feat, act (and the BPTT state when training).
 static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const float* z, int ldz, int m, int t,
                           cudaStream_t st) {
     const auto& T = l->tensors;
-    const int mode = l->cfg.gemm_mode;
+    // inference workspaces carry no GEMM workspace: actor batches are small and run on the fp32 FFMA kernels
+    const int mode = w->gemm_ws ? l->cfg.gemm_mode : FI_GEMM_SIMT;
     const int rt = m * t;
     {
         LaunchScope ls("transpose_whh_kernel", st, 2.0 * 4 * kG4 * kLstmH, kWorkBytes);
@@ -341,8 +388,19 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         FI_TRY(ls.done());
     }
     // gates = z W_ih^T + b_ih for all B*T rows at once
-    FI_TRY(launch_gemm(mode, 0, rt, kG4, kZDim, z, ldz, params + T[0].offset, kZDim, w->gates, kG4, params + T[2].offset,
-                       0, nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    if (farmer_use_half(l, w, rt)) {
+        FI_TRY(launch_zero2(w->hs, 4 * sizeof(HScale), nullptr, 0, st));
+        FI_TRY(launch_amax(z, ldz, (size_t)rt, kZDim, w->hs + kHsObs, st));
+        FI_TRY(launch_amax(params + T[0].offset, kZDim, kG4, kZDim, w->hs + kHsWih, st));
+        FI_TRY(launch_split_h(z, ldz, (size_t)rt, kZDim, kObsLdH, w->obs_hi, w->obs_lo, w->hs + kHsObs, 1, st));
+        FI_TRY(launch_split_h(params + T[0].offset, kZDim, kG4, kZDim, kObsLdH, w->wih_hi, w->wih_lo, w->hs + kHsWih, 1, st));
+        const SplitMat a{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, b{w->wih_hi, w->wih_lo, kObsLdH, w->hs + kHsWih};
+        FI_TRY(launch_gemm_tc_split(0, rt, kG4, kZDim, a, b, TcOut{w->gates, kG4, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
+                                    params + T[2].offset, 0, nullptr, 0, nullptr, 0, st));
+    } else {
+        FI_TRY(launch_gemm(mode, 0, rt, kG4, kZDim, z, ldz, params + T[0].offset, kZDim, w->gates, kG4, params + T[2].offset,
+                           0, nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    }
     {
         // recurrent flops: 2 * 128 * 512 per (row, step)
         LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
@@ -421,12 +479,26 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         FI_TRY(ls.done());
     }
     const int rt = m * t;
-    FI_TRY(launch_gemm(mode, 2, kG4, kZDim, rt, w->gates, kG4, batch, kRecWords, g + T[0].offset, kZDim, nullptr, 0, nullptr,
-                       0, w->gemm_ws, w->gemm_ws_bytes, st));
-    FI_TRY(launch_gemm(mode, 2, kG4, kLstmH, rt, w->gates, kG4, w->hprev, kLstmH, g + T[1].offset, kLstmH, nullptr, 0,
-                       nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    if (farmer_use_half(l, w, rt)) {
+        // dW_ih = dgates^T z, dW_hh = dgates^T h_prev: the gate gradients are split once and read MN-major by both
+        FI_TRY(launch_amax(w->gates, kG4, (size_t)rt, kG4, w->hs + kHsDg, st));
+        FI_TRY(launch_amax(w->hprev, kLstmH, (size_t)rt, kLstmH, w->hs + kHsHp, st));
+        FI_TRY(launch_split_h(w->gates, kG4, (size_t)rt, kG4, kG4, w->dg_hi, w->dg_lo, w->hs + kHsDg, 1, st));
+        FI_TRY(launch_split_h(w->hprev, kLstmH, (size_t)rt, kLstmH, kLstmH, w->hp_hi, w->hp_lo, w->hs + kHsHp, 1, st));
+        const SplitMat dg{w->dg_hi, w->dg_lo, kG4, w->hs + kHsDg};
+        const SplitMat obs{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, hp{w->hp_hi, w->hp_lo, kLstmH, w->hs + kHsHp};
+        FI_TRY(launch_gemm_tc_split(2, kG4, kZDim, rt, dg, obs, TcOut{g + T[0].offset, kZDim, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
+                                    nullptr, 0, nullptr, 0, w->split_ws, w->split_ws_bytes, st));
+        FI_TRY(launch_gemm_tc_split(2, kG4, kLstmH, rt, dg, hp, TcOut{g + T[1].offset, kLstmH, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
+                                    nullptr, 0, nullptr, 0, w->split_ws, w->split_ws_bytes, st));
+    } else {
+        FI_TRY(launch_gemm(mode, 2, kG4, kZDim, rt, w->gates, kG4, batch, kRecWords, g + T[0].offset, kZDim, nullptr, 0, nullptr,
+                           0, w->gemm_ws, w->gemm_ws_bytes, st));
+        FI_TRY(launch_gemm(mode, 2, kG4, kLstmH, rt, w->gates, kG4, w->hprev, kLstmH, g + T[1].offset, kLstmH, nullptr, 0,
+                           nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
+    }
     FI_TRY(launch_colsum(w->gates, kG4, rt, kG4, g + T[2].offset, w->colsum_ws, w->colsum_ws_bytes, st));
-    FI_CUDA_OK(cudaMemcpyAsync(g + T[3].offset, g + T[2].offset, kG4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FI_TRY(launch_copy_words(g + T[3].offset, g + T[2].offset, kG4, st));   // d b_hh = d b_ih (a kernel: no copy engine on this stream)
     return FI_OK;
 }
 

@@ -206,7 +206,7 @@ def _farmer_learner(fi, m, t, **kw):
     return fi.Learner(1, max(m, 2), t, m, 0, 0, "", "", 0, model="farmer_lstm", **kw)
 
 
-@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("gemm_mode", ["simt", "auto", "tcgen05_f16"])
 @pytest.mark.parametrize("ci", [3, 4, 5, 6])
 def test_farmer_step_vs_reference_golden(fi, oracle, ci, gemm_mode):
     """The CUDA FarmerLstm step against the reference's own libtorch train_step
