@@ -1,35 +1,42 @@
-// tcgen05 3xTF32 GEMM for sm_100a: fp32-accurate products on the 5th-generation tensor cores.
+// tcgen05 GEMM for sm_100a with fp32-accurate products on the 5th-generation tensor cores: every operand is carried as a
+// pair of 11-bit-significand numbers and every product costs three tensor-core products. Two operand formats, one kernel
+// (template parameter H):
 //
-// The learner's tolerance (parameters within 1e-5 of an fp32/float64 reference) rules out plain
-// TF32 / bf16 operands, so every fp32 operand x is carried as an exact pair
-//     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
-//                    lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits),
-// and each product needs three kind::tf32 products:
+//   3xTF32 (H = 0)  x = hi + lo, hi = x with the low 13 mantissa bits cleared (a TF32 number), lo = x - hi; fp32 arrays.
+//   3xFP16 (H = 1)  x * s = hi + lo' / 2048 with hi, lo' fp16 arrays and s a per-tensor power of two kept on the device
+//                   (HScale): kind::f16 MMAs run at twice the kind::tf32 rate on half the shared-memory bytes per
+//                   reduction element. The scale of a GEMM output is derived on the device, before the GEMM runs, from the
+//                   bound k * max|A| * max|B| (+ max|bias|) so nothing can overflow fp16; each epilogue measures the true
+//                   max |x| of what it wrote so that bounds stay one layer loose. See DESIGN.md 3.1 for the error analysis.
+//
+// The learner's tolerance (parameters within 1e-5 of an fp32/float64 reference) rules out plain TF32 / bf16 operands. Each
+// product needs
 //     main += A_hi B_hi            corr += A_hi B_lo + A_lo B_hi      (A_lo B_lo ~ 2^-22 relative is dropped),
 // issued as TWO instructions per k-slice: B_hi and B_lo tiles are adjacent in shared memory, so one N = 2*BN MMA
 // computes A_hi [B_hi | B_lo] into [main | corr] (adjacent TMEM columns) and one N = BN MMA adds A_lo B_hi to corr.
 // Measured on B200: the tensor core adds into its fp32 accumulator with truncation towards zero, a few ulp
 // of the running sum per MMA (error grew linearly with K: 2.4e-5 at K=32, 4.6e-4 at K=512 on sums of
 // magnitude ~20 when one accumulator took all of K). The products therefore accumulate in TMEM only over
-// a CHUNK of 4 k-blocks (K = 128); the promotion warps then add the chunk (main + corr) to fp32 register
-// accumulators with round-to-nearest (the scheme of Ootomo & Yokota 2022, at chunk granularity): 6.5e-5 at
-// K=512 (1.7e-6 of the largest sum). Halving the chunk only gave 5.0e-5: what is left is the truncation
-// inside each MMA's own 8-term sum, which no promotion schedule removes.
+// a CHUNK of K = 128 (4 k-blocks of 32 tf32 / 2 k-blocks of 64 fp16); the promotion warps then add the chunk
+// (main + corr, corr scaled by 2^-11 in the fp16 format) to fp32 register accumulators with round-to-nearest (the scheme
+// of Ootomo & Yokota 2022, at chunk granularity): 6.5e-5 at K=512 (1.7e-6 of the largest sum). Halving the chunk only
+// gave 5.0e-5: what is left is the truncation inside each MMA's own sum, which no promotion schedule removes.
 //
 // Kernel anatomy (one CTA per SM, persistent over output tiles; 128 control threads + 4 or 8 promotion warps):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A_hi, A_lo, B_hi, B_lo into a
 //              multi-stage shared-memory ring, completion on mbarriers;
-//   warp 1     MMA issuer: one elected lane issues 2 tcgen05.mma (M=128, K=8; N=2*BN and N=BN) x 4 k-slices per
-//              32-wide k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
+//   warp 1     MMA issuer: one elected lane issues 2 tcgen05.mma (M=128; N=2*BN and N=BN) x 4 k-slices of 32 bytes per
+//              k-block; tcgen05.commit releases the smem stage / publishes a finished chunk;
 //   warp 2     TMEM allocator: 2 chunk buffers of [main | corr] = 2*BN fp32 columns each, so the promotion of
 //              chunk i overlaps the MMAs of chunk i+1 and the epilogue of tile j those of tile j+1;
 //   warps 4..  promotion + epilogue, two warps per TMEM lane quarter (each owns half of the tile's columns):
-//              tcgen05.ld (32 lanes x 32 columns) into register accumulators, then bias / ReLU / ReLU-mask and
-//              either a plain fp32 store or the hi/lo split store (TMA) that feeds the next GEMM.
-// Operand layouts (UMMA "major"): K-major tiles are [rows][32 k] with one 128-byte row per matrix row (128B
-// swizzle, 16-byte atoms); MN-major tiles are [32 k][32 mn] boxes (the reduction index is the slow one; tf32 only
-// supports the 128B swizzle with 32-byte atoms there), so dgrad (B = W[n,k] read along n) and wgrad (both operands
-// read along the batch rows) need no transposed copies.
+//              tcgen05.ld (32 lanes x 32 columns) into register accumulators, then bias (through the accumulator's
+//              initial value) / ReLU / ReLU-mask and either a plain fp32 store or the hi/lo split store (TMA) that feeds
+//              the next GEMM.
+// Operand layouts (UMMA "major"): K-major tiles are [rows][128 bytes of k] (128B swizzle, 16-byte atoms); MN-major tiles
+// are boxes of [k][128 bytes of mn] (the reduction index is the slow one): tf32 only supports the 128B swizzle with
+// 32-byte atoms there ([32 k][32 mn] boxes), fp16 uses the ordinary one ([64 k][64 mn] boxes). So dgrad (B = W[n,k] read
+// along n) and wgrad (both operands read along the batch rows) need no transposed copies.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
