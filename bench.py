@@ -329,7 +329,8 @@ def run_b200_arm(args):
         ring = L.getSharedBuffers()[0]
         cores_per_rank = max(1, (os.cpu_count() or 8) // world)
         nw_copy = args.writers if args.writers > 0 else max(2, min(16, cores_per_rank))
-        nw_zc = 2  # in-place producers only take the ring lock: two threads keep the ring full
+        nw_zc = int(os.environ.get("FI_BENCH_ZC_THREADS", "2"))  # in-place producers only take the ring lock: two threads keep the ring full
+        zc_burst = int(os.environ.get("FI_BENCH_ZC_BURST", "64"))
 
         def copy_writer(j: int, steps: int, nw: int):
             # actor thread j owns trajectories [j*per, (j+1)*per) of every step: SharedBuffer::write semantics (the ring
@@ -345,7 +346,7 @@ def run_b200_arm(args):
             # zero-copy producer (fi_ring_reserve_many / fi_ring_commit_many): the trajectory is produced IN the pinned slot
             # (what an MPI_Irecv posted into the slot does); here the slot keeps the synthetic trajectory written during
             # warm-up and the producer stamps the step number into an unused word of the first record of each burst
-            burst = 64
+            burst = zc_burst
             for s in range(steps):
                 for i in range(j * burst, M, nw * burst):
                     n = min(burst, M - i)

@@ -84,8 +84,16 @@ struct fi_ring {
     size_t copy_index = 0, uncopied = 0;  // published slots [copy_index, copy_index + uncopied) are not in HBM yet
     std::vector<unsigned char> committed;  // per slot: writer finished filling the pinned slot
     std::vector<size_t> commit_bytes;
-    cudaEvent_t gather_done = nullptr;  // last gather has finished reading the HBM slots
-    bool gather_pending = false;
+    // Gathers read HBM slots that a later H2D copy will overwrite. Each gather gets a sequence number and an event (a
+    // small ring of events); every slot remembers the last gather that read it, and the side stream waits for a gather
+    // only before a copy run that overwrites slots that gather read. (One global "wait for the last gather" gate made
+    // the copies of batches s+1.. wait until the learner stream reached gather(s), i.e. for the end of step s-1: the
+    // copy engine then had only one step time per batch and stood idle the rest.)
+    static constexpr int kGatherEvents = 8;
+    cudaEvent_t gather_ev[kGatherEvents] = {};
+    uint64_t gather_seq = 0;              // gathers issued so far
+    uint64_t side_waited_seq = 0;         // the side stream is already ordered behind gathers <= this
+    std::vector<uint64_t> slot_gather_seq;  // per slot: sequence number of the last gather that read it (0: none)
 
     std::mutex mu;
     std::condition_variable not_full, not_empty;
@@ -133,7 +141,9 @@ fi_ring* fi_ring_create(int device, size_t entry_size, size_t capacity) {
     r->h2d_done.assign(capacity, nullptr);
     for (size_t i = 0; i < capacity; i++)
         if ((e = cudaEventCreateWithFlags(&r->h2d_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&r->gather_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (cudaEvent_t& ev : r->gather_ev)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    r->slot_gather_seq.assign(capacity, 0);
     if ((e = cudaEventCreateWithFlags(&r->h2d_tail, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     r->h2d_ref.resize(capacity);
     for (size_t i = 0; i < capacity; i++) r->h2d_ref[i] = i;
@@ -149,7 +159,8 @@ void fi_ring_destroy(fi_ring* r) {
     if (r->learner) cudaStreamSynchronize(r->learner);
     for (auto ev : r->h2d_done)
         if (ev) cudaEventDestroy(ev);
-    if (r->gather_done) cudaEventDestroy(r->gather_done);
+    for (cudaEvent_t ev : r->gather_ev)
+        if (ev) cudaEventDestroy(ev);
     if (r->h2d_tail) cudaEventDestroy(r->h2d_tail);
     if (r->side) cudaStreamDestroy(r->side);
     if (r->learner) cudaStreamDestroy(r->learner);
@@ -167,10 +178,6 @@ constexpr size_t kH2DRunBytes = (size_t)4 << 20;    // ... or this many bytes, w
 static void ring_flush_locked(fi_ring* r, bool force) {
     if (r->uncopied == 0) return;
     if (!force && r->uncopied < kH2DRunSlots && r->uncopied * r->slot_bytes < kH2DRunBytes) return;
-    if (r->gather_pending) {  // the HBM slots may still be being read by the last gather
-        cudaStreamWaitEvent(r->side, r->gather_done, 0);
-        r->gather_pending = false;  // the side stream is ordered behind it from now on
-    }
     cudaError_t e = cudaSuccess;
     while (r->uncopied > 0 && e == cudaSuccess) {
         const size_t first = r->copy_index;
@@ -183,6 +190,16 @@ static void ring_flush_locked(fi_ring* r, bool force) {
             bytes = 0;
         }
         const size_t full = (bytes == 0 && r->commit_bytes[first + len - 1] == r->slot_bytes) ? len : len - 1;
+        // the HBM slots of this run may still be read by a gather that has not run yet
+        uint64_t need = 0;
+        for (size_t i = first; i < first + len; i++)
+            if (r->slot_gather_seq[i] > need) need = r->slot_gather_seq[i];
+        if (need > r->side_waited_seq) {
+            // an event slot re-recorded by a newer gather only makes this wait longer (same stream order), never unsafe
+            e = cudaStreamWaitEvent(r->side, r->gather_ev[need % fi_ring::kGatherEvents], 0);
+            r->side_waited_seq = need;
+        }
+        if (e != cudaSuccess) break;
         if (full > 0)
             e = cudaMemcpyAsync(r->dev_slots + first * r->slot_bytes, r->host_slots + first * r->slot_bytes,
                                 full * r->slot_bytes, cudaMemcpyHostToDevice, r->side);
@@ -360,12 +377,17 @@ int fi_ring_read_batch(fi_ring* r, size_t batch_size, void* stream, fi_batch* ou
         r->batch_cap = batch_size;
     }
     const size_t first = r->read_index;
-    // every published slot goes to HBM now; copies are issued in FIFO order on one stream, so the tail event covers all
+    // every published slot goes to HBM now. Copies are issued in FIFO order on one stream, so the event of the run that
+    // holds this batch's LAST slot covers the whole batch; waiting for the tail instead would also wait for the slots
+    // producers have already committed for later batches (they run up to capacity - M slots ahead), i.e. stall the
+    // learner behind host->device traffic it does not need yet
     ring_flush_locked(r, true);
-    FI_CUDA_OK(cudaStreamWaitEvent(st, r->h2d_tail, 0));
+    const size_t last_slot = (first + batch_size - 1) % r->capacity;
+    FI_CUDA_OK(cudaStreamWaitEvent(st, r->h2d_done[r->h2d_ref[last_slot]], 0));
     FI_TRY(fi::launch_gather(r->dev_slots, r->capacity, r->slot_bytes, first, batch_size, r->dev_batch, st));
-    FI_CUDA_OK(cudaEventRecord(r->gather_done, st));
-    r->gather_pending = true;
+    const uint64_t seq = ++r->gather_seq;
+    FI_CUDA_OK(cudaEventRecord(r->gather_ev[seq % fi_ring::kGatherEvents], st));
+    for (size_t i = 0; i < batch_size; i++) r->slot_gather_seq[(first + i) % r->capacity] = seq;
     r->read_index = (first + batch_size) % r->capacity;
     r->count -= batch_size;
     out->dev_ptr = r->dev_batch;
