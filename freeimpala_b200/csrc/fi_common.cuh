@@ -135,6 +135,22 @@ private:
     bool active_ = false;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device), safe
+// against several player threads (or learners on different devices) reaching the first launch together.
+inline int ensure_dynamic_smem(std::atomic<uint64_t>& done_devices, const void* kernel, int bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done_devices.load(std::memory_order_acquire) & bit) return FI_OK;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (done_devices.load(std::memory_order_relaxed) & bit) return FI_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return set_error(FI_ERR_CUDA, "cudaFuncSetAttribute(%d B of shared memory) failed: %s", bytes, cudaGetErrorString(e));
+    done_devices.fetch_or(bit, std::memory_order_release);
+    return FI_OK;
+}
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

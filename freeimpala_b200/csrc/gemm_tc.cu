@@ -1041,11 +1041,8 @@ size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k) {
 template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H>
 static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEpilogue& ep, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FI_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_devices{0};
+    FI_TRY(ensure_dynamic_smem(attr_devices, (const void*)gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, Cfg::kSmemBytes));
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
     const char* label = H ? (!B_MN ? "gemm_tc_kernel<f16x3,NT>" : (!A_MN ? "gemm_tc_kernel<f16x3,NN>" : "gemm_tc_kernel<f16x3,TN>"))
                           : (!B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>"));

@@ -404,11 +404,8 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
     {
         // recurrent flops: 2 * 128 * 512 per (row, step)
         LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
-        static bool fwd_attr = false;
-        if (!fwd_attr) {
-            FI_CUDA_OK(cudaFuncSetAttribute(lstm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmFwdSmem));
-            fwd_attr = true;
-        }
+        static std::atomic<uint64_t> fwd_attr{0};
+        FI_TRY(ensure_dynamic_smem(fwd_attr, (const void*)lstm_forward_kernel, (int)kLstmFwdSmem));
         lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
             w->gates, w->whh_t, params + T[3].offset, m, t, w->hprev, w->cst, w->feat);
         FI_TRY(ls.done());
@@ -469,11 +466,8 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
     // d = dfeat [m, 612]; BPTT turns the stored gates into pre-activation gate gradients
     {
         LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
-        static bool bwd_attr = false;
-        if (!bwd_attr) {
-            FI_CUDA_OK(cudaFuncSetAttribute(lstm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmBwdSmem));
-            bwd_attr = true;
-        }
+        static std::atomic<uint64_t> bwd_attr{0};
+        FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
         lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset,
                                                                                       w->cst, d, kFeat, m, t);
         FI_TRY(ls.done());
