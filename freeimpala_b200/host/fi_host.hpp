@@ -141,6 +141,10 @@ public:
     std::shared_ptr<ModelManager> getModelManager() { return model_manager_; }                   // learner.h:205-207
     fi_learner* handle() const { return h_; }
     size_t iterationsDone(size_t p) const { return iterations_[p]; }
+    // Losses of player p's optimiser step `step` (1-based, one of the last 8): {total, pg, baseline, entropy} for V-trace,
+    // {loss,0,0,0} for the regression step. Waits only for that step's read-back (no counterpart in the reference, whose
+    // trainModel computes nothing to log).
+    bool lossesAt(size_t p, uint64_t step, float out[4]) const { return fi_learner_losses_at(h_, (int)p, step, out) == FI_OK; }
 
 private:
     void trainModel(size_t p, const DeviceBatch& batch) {                      // learner.h:32-49
