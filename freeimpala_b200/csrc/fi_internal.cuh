@@ -6,6 +6,9 @@ namespace fi {
 
 int launch_gather(const void* ring_base, size_t capacity, size_t slot_bytes, size_t first, size_t m, void* dst,
                   cudaStream_t stream);
+// ring.cu: the consumer of a gathered batch tells the owning ring (looked up by the batch pointer; no-op for other pointers)
+// that every read of it has been enqueued on `consumer`, so that the ring's next gather is ordered behind them
+int ring_note_consumed(const void* dev_ptr, cudaStream_t consumer);
 int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v,
                float grad_scale, cudaStream_t stream, float* snapshot = nullptr, const double* losses_src = nullptr,
                double* losses_dst = nullptr);

@@ -83,6 +83,23 @@ struct TcEpilogue {
 struct TcShape {
     int m, n, k;
     int num_m_blocks, num_n_blocks, num_splits, kb_per_split, num_kb;
+    int dbg;  // FI_TC_DBG knock-out bits (tools/gemm_knockout.py; results are garbage, timings say what bounds the kernel):
+              // 1 no TMA loads, 2 no MMAs, 4 no promotion loads, 8 no epilogue, 16 no A_lo B_hi MMA, 32 no TMA stores
+    unsigned long long* trace;  // FI_TC_TRACE: per-role event log of the first CTAs (tools/gemm_trace.py), else null
+};
+
+// ---- pipeline trace (diagnostics) ----------------------------------------------------------------------------
+// CTAs 0..kTraceCtas-1 log (clock64 << 8 | tag) per role: role 0 TMA producer, 1 MMA issuer, 2 first promotion warp.
+constexpr int kTraceCtas = 4, kTraceRoles = 3, kTraceCap = 4096;
+struct TraceLog {
+    unsigned long long* p = nullptr;
+    int n = 0;
+    __device__ __forceinline__ void init(unsigned long long* base, int role) {
+        if (base && blockIdx.x < kTraceCtas) p = base + ((size_t)blockIdx.x * kTraceRoles + role) * kTraceCap;
+    }
+    __device__ __forceinline__ void ev(unsigned tag) {
+        if (p && n < kTraceCap) p[n++] = ((unsigned long long)clock64() << 8) | tag;
+    }
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -168,6 +185,16 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// One elected lane of a converged warp (elect.sync): the role loops of the producer and issuer warps run warp-uniformly --
+// every operand of the TMA / tcgen05 instructions then lives in uniform registers -- and only the asynchronous
+// instructions themselves sit under this predicate. (Round 1 ran those loops inside `if (lane == 0)`: the compiler had to
+// move the five operands of every UTCHMMA from vector to uniform registers with an ELECT + R2UR.BROADCAST waterfall loop,
+// ~60 clocks per MMA: the issuer needed ~970 clocks per k-block for 768 clocks of tensor-core work; profiles/r2_gemm_trace.md.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -314,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto main_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
     auto main_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index: provably warp-uniform
     float tmax_kernel = 0.f;  // fp16 format: running max |output| of this thread (published once at the end)
     const int tiles = sh.num_m_blocks * sh.num_n_blocks;
     const int total_work = tiles * sh.num_splits;
@@ -351,14 +378,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // TMEM columns of chunk buffer b: main at [2b*BN, 2b*BN + BN), corr at [2b*BN + BN, 2b*BN + 2BN)
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform; the loads are issued by one elected lane) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
                 if constexpr (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1);
                 else tma_load_2d(dst, map, bar, c0, c1);
             };
+            TraceLog tl;
+            if (lane == 0) tl.init(sh.trace, 0);
             for (int w = unit; w < total_work; w += num_units) {
                 const int tile = w % tiles, split = w / tiles;
                 // this CTA's rows of A and rows of the B tile (pair mode: the second CTA takes the second half of each)
@@ -367,12 +396,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
+                    tl.ev(1);
                     const uint32_t bar = full_bar(stage);
-                    // pair mode: both CTAs' loads are credited to the leader's barrier, which expects both stages
-                    if (!PAIR || cta_rank == 0) mbar_expect_tx(bar, (PAIR ? 2 : 1) * Cfg::kStageBytes);
+                    if (!PAIR && (sh.dbg & 1)) {
+                        if (elect_one()) mbar_arrive(bar);
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes;
                     const uint32_t b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
                     const int k0 = kb * BK;
+                    if (elect_one()) {
+                    // pair mode: both CTAs' loads are credited to the leader's barrier, which expects both stages
+                    if (!PAIR || cta_rank == 0) mbar_expect_tx(bar, (PAIR ? 2 : 1) * Cfg::kStageBytes);
                     if constexpr (!A_MN) {
                         load(a_hi, &map_a_hi, bar, k0, m0);
                         load(a_lo, &map_a_lo, bar, k0, m0);
@@ -393,13 +430,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             load(b_lo + j * kBoxBytes, &map_b_lo, bar, n0 + j * kBoxMN, k0);
                         }
                     }
+                    }
+                    __syncwarp();
+                    tl.ev(2);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && cta_rank == 0) {
+        // ===================== MMA issuer (warp-uniform; MMAs and commits are issued by one elected lane) =====================
+        if (cta_rank == 0) {
+            const uint32_t tmem_base_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);   // a value the compiler knows to be warp-uniform
             constexpr uint32_t idesc_wide = umma_idesc(kTcBM, 2 * BN, A_MN ? 1 : 0, B_MN ? 1 : 0, H ? 1 : 0);  // A_hi [B_hi | B_lo]
             constexpr uint32_t idesc_half = umma_idesc(kTileM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, H ? 1 : 0);      // A_lo B_hi (pair: every product)
             // K-major (128B swizzle, 16 B atoms): a k-slice of 8 fp32 is 32 bytes inside the 128-byte row; 8-row groups
@@ -428,16 +469,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             auto desc = [](uint32_t hi_word, uint32_t lo_word) { return ((uint64_t)hi_word << 32) | lo_word; };
             int stage = 0, mb = 0;
             uint32_t phase = 0, mphase = 0;
+            TraceLog tl;
+            if (lane == 0) tl.init(sh.trace, 1);
             for (int w = unit; w < total_work; w += num_units) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kc = kb0; kc < kb1; kc += kChunk) {
                     mbar_wait(main_empty_bar(mb), mphase ^ 1);
+                    tl.ev(10);
                     tc_fence_after();
-                    const uint32_t tmem_main = tmem_base + (uint32_t)(mb * 2 * BN), tmem_corr = tmem_main + BN;
+                    const uint32_t tmem_main = tmem_base_u + (uint32_t)(mb * 2 * BN), tmem_corr = tmem_main + BN;
                     const int kce = min(kb1, kc + kChunk);
                     for (int kb = kc; kb < kce; kb++) {
                         mbar_wait(full_bar(stage), phase);
+                        tl.ev(11);
                         tc_fence_after();
                         const uint32_t a_hi = smem_base + stage * Cfg::kStageBytes, a_lo = a_hi + kABytes, b_hi = a_lo + kABytes;
                         const uint32_t b_lo = b_hi + kBBytes;
@@ -446,6 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint32_t la_lo = ((a_lo >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
                         const uint32_t lb_hi = ((b_hi >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
                         const uint32_t lb_lo = ((b_lo >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+                        if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {  // 4 k-slices of 32 bytes (8 tf32 / 16 fp16) per k-block
                             const uint64_t da_hi = desc(a_hi_word, la_hi + ks * a_step);
@@ -461,17 +507,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 mma(tmem_corr, da_lo, db, idesc_half, 1u);        // corr  += A_lo B_hi
                             } else {
                                 (void)lb_lo;
-                                mma(tmem_main, da_hi, db, idesc_wide, first);  // [main | corr] (+)= A_hi [B_hi | B_lo]
-                                mma(tmem_corr, da_lo, db, idesc_half, 1u);     // corr += A_lo B_hi
+                                if (!(sh.dbg & 2)) mma(tmem_main, da_hi, db, idesc_wide, first);  // [main | corr] (+)= A_hi [B_hi | B_lo]
+                                if (!(sh.dbg & 18)) mma(tmem_corr, da_lo, db, idesc_half, 1u);    // corr += A_lo B_hi
                             }
                         }
+                        tl.ev(12);
                         // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
                         if constexpr (PAIR) tc_commit_pair(empty_bar(stage));
                         else tc_commit(empty_bar(stage));
+                        }
+                        __syncwarp();
+                        tl.ev(13);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    if constexpr (PAIR) tc_commit_pair(main_full_bar(mb));  // chunk complete, published to both CTAs
-                    else tc_commit(main_full_bar(mb));
+                    if (elect_one()) {
+                        if constexpr (PAIR) tc_commit_pair(main_full_bar(mb));  // chunk complete, published to both CTAs
+                        else tc_commit(main_full_bar(mb));
+                    }
+                    __syncwarp();
+                    tl.ev(14);
                     if (++mb == 2) { mb = 0; mphase ^= 1; }
                 }
             }
@@ -506,6 +560,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
         }
+        TraceLog tl;
+        if (pw == 0 && lane == 0) tl.init(sh.trace, 2);
         float bias_next[CW / 32];
 #pragma unroll
         for (int c = 0; c < CW / 32; c++) bias_next[c] = 0.f;
@@ -549,7 +605,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             for (int kc = kb0; kc < kb1; kc += kChunk) {
                 mbar_wait(main_full_bar(mb), mphase);
+                tl.ev(20);
                 tc_fence_after();
+                if (!(sh.dbg & 4))
 #pragma unroll
                 for (int c = 0; c < CW / 32; c++) {
                     uint32_t v[32], u[32];
@@ -567,8 +625,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if constexpr (PAIR) mbar_arrive_cluster(mb ? leader_main_empty1 : leader_main_empty0);  // the MMA issuer lives in CTA 0
                     else mbar_arrive(main_empty_bar(mb));
                 }
+                tl.ev(21);
                 if (++mb == 2) { mb = 0; mphase ^= 1; }
             }
+            tl.ev(22);   // tile's k loop done: the epilogue runs until the next tag 20
+            if (sh.dbg & 8) continue;
             if constexpr (H) {
 #pragma unroll
                 for (int i = 0; i < CW; i++) acc[i] *= out_mul;   // powers of two: exact
@@ -621,6 +682,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     }
                                 }
                             }
+                            tl.ev(23);
                             // hi parts first: converted, staged and handed to the TMA; the lo' parts (the longer arithmetic) are
                             // computed while that bulk store reads the staging tile, so the wait before reusing it is short
                             uint32_t wh[32];
@@ -635,18 +697,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             }
                             // max |output| from the rounded hi parts (within 2^-11 of the exact value; consumers only use it in bounds)
                             tmax_kernel = fmaxf(tmax_kernel, fmaxf(__low2float(hmax), __high2float(hmax)) * (1.001f / out_scale));
+                            tl.ev(24);
                             if (lane == 0) tma_store_wait_read();   // the previous tile's lo' store: long finished
                             __syncwarp();
+                            tl.ev(25);
 #pragma unroll
                             for (int j = 0; j < 8; j++)   // 16-byte chunk j = columns 8j .. 8j+7, 128B swizzle
                                 st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
                                               make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) {
+                            if (lane == 0 && !(sh.dbg & 32)) {
                                 tma_store_2d(&map_c_hi, stage_tile, colw0, rbase);
                                 tma_store_commit();
                             }
+                            tl.ev(26);
 #pragma unroll
                             for (int e = 0; e < 32; e++) {
                                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&wh[e]));
@@ -654,18 +719,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 const __half2 lo2 = __floats2half2_rn(fmaf(acc[2 * e], 2048.f, -2048.f * hf.x), fmaf(acc[2 * e + 1], 2048.f, -2048.f * hf.y));
                                 wh[e] = *reinterpret_cast<const uint32_t*>(&lo2);
                             }
+                            tl.ev(27);
                             if (lane == 0) tma_store_wait_read();
                             __syncwarp();
+                            tl.ev(28);
 #pragma unroll
                             for (int j = 0; j < 8; j++)
                                 st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
                                               make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) {
+                            if (lane == 0 && !(sh.dbg & 32)) {
                                 tma_store_2d(&map_c_lo, stage_tile, colw0, rbase);
                                 tma_store_commit();
                             }
+                            tl.ev(29);
                         }
                     }
                     continue;
@@ -995,6 +1063,24 @@ static int make_map_uncached(CUtensorMap* map, const void* base, uint64_t inner,
     return FI_OK;
 }
 
+// FI_TC_TRACE="<trans>,<min n>,<min k>": launches of that operand-major combination with n >= min n and k >= min k log their
+// pipeline events into a device buffer (each matching launch starts a fresh log); fi_debug_tc_trace copies it out.
+static unsigned long long* g_tc_trace = nullptr;
+static unsigned long long* tc_trace_buffer(int trans, int /*m*/, int n, int k) {
+    struct Filter { int on, trans, n, k; };
+    static const Filter f = [] {
+        const char* e = getenv("FI_TC_TRACE");
+        Filter r{0, 0, 0, 0};
+        if (e) r.on = sscanf(e, "%d,%d,%d", &r.trans, &r.n, &r.k) >= 1;
+        return r;
+    }();
+    if (!f.on || trans != f.trans || n < f.n || k < f.k) return nullptr;
+    const size_t bytes = (size_t)kTraceCtas * kTraceRoles * kTraceCap * sizeof(unsigned long long);
+    if (!g_tc_trace && cudaMalloc((void**)&g_tc_trace, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(g_tc_trace, 0, bytes);   // legacy-stream memset: diagnostics only
+    return g_tc_trace;
+}
+
 static int pick_bn(int n, bool half = false) { return n > 64 ? 128 : ((n > 32 || half) ? 64 : 32); }
 
 // CTA-pair mode (cta_group::2, 256 x 128 tiles). Measured at the bench shape (profiles/r1_gemm_tc.md): the split-K
@@ -1044,7 +1130,11 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
     static std::atomic<uint64_t> attr_devices{0};
     FI_TRY(ensure_dynamic_smem(attr_devices, (const void*)gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, Cfg::kSmemBytes));
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
-    const char* label = H ? (!B_MN ? "gemm_tc_kernel<f16x3,NT>" : (!A_MN ? "gemm_tc_kernel<f16x3,NN>" : "gemm_tc_kernel<f16x3,TN>"))
+    // (the odd-shaped products of a learner step -- layer 1's short K, the 17-wide head -- are timed under their own names)
+    const bool narrow = sh.n < 64, short_k = !A_MN && sh.k < 256;
+    const char* label = H ? (!B_MN ? (narrow ? "gemm_tc_kernel<f16x3,NT,head>" : short_k ? "gemm_tc_kernel<f16x3,NT,k162>" : "gemm_tc_kernel<f16x3,NT>")
+                                   : (!A_MN ? (short_k ? "gemm_tc_kernel<f16x3,NN,head>" : "gemm_tc_kernel<f16x3,NN>")
+                                            : (narrow ? "gemm_tc_kernel<f16x3,TN,head>" : sh.n < 256 ? "gemm_tc_kernel<f16x3,TN,n162>" : "gemm_tc_kernel<f16x3,TN>")))
                           : (!B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>"));
     LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
     if constexpr (PAIR) {
@@ -1086,6 +1176,9 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     sh.num_n_blocks = (n + bn - 1) / bn;
     sh.num_kb = (k + bk - 1) / bk;
     sh.num_splits = tc_splits(trans, m, n, k, pair, half);
+    static const int dbg_flags = [] { const char* e = getenv("FI_TC_DBG"); return e ? atoi(e) : 0; }();
+    sh.dbg = dbg_flags;
+    sh.trace = tc_trace_buffer(trans, m, n, k);
     TcEpilogue ep;
     ep.c = out.c; ep.ldc = out.ldc; ep.c_hi = out.c_hi; ep.c_lo = out.c_lo; ep.ldc_split = out.ld_split;
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
@@ -1166,6 +1259,15 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
 
 bool gemm_tc_available() { return encode_fn() != nullptr; }
 
+int tc_trace_copy(void* host, size_t bytes) {
+    const size_t have = (size_t)kTraceCtas * kTraceRoles * kTraceCap * sizeof(unsigned long long);
+    if (!g_tc_trace) return set_error(FI_ERR_STATE, "no tcgen05 trace was recorded (set FI_TC_TRACE)");
+    if (bytes < have) return set_error(FI_ERR_ARG, "trace buffer needs %zu bytes", have);
+    FI_CUDA_OK(cudaDeviceSynchronize());
+    FI_CUDA_OK(cudaMemcpy(host, g_tc_trace, have, cudaMemcpyDeviceToHost));
+    return (int)(have / sizeof(unsigned long long));
+}
+
 // ---- plain fp32 entry (fi_op_gemm, FarmerLstm dense stack): split the operands into the workspace first --------
 static size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1245,3 +1347,6 @@ int launch_gemm_h(int trans, int m, int n, int k, const float* a, int lda, const
 }
 
 }  // namespace fi
+
+// Diagnostics: the pipeline event log of the last traced tcgen05 GEMM launch (see FI_TC_TRACE above).
+extern "C" int fi_debug_tc_trace(void* host, size_t bytes) { return fi::tc_trace_copy(host, bytes); }

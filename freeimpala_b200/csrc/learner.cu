@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include <sys/stat.h>
 
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -282,6 +283,18 @@ int create_player(fi_learner* l, int index) {
     return publish_sync(p, p->version);
 }
 
+// mkdir -p
+bool make_dirs(const std::string& path) {
+    if (path.empty()) return false;
+    for (size_t i = 1; i <= path.size(); i++) {
+        if (i != path.size() && path[i] != '/') continue;
+        const std::string part = path.substr(0, i);
+        if (mkdir(part.c_str(), 0777) != 0 && errno != EEXIST) return false;
+    }
+    struct stat st;
+    return stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
 bool file_exists(const std::string& path) {
     struct stat st;
     return stat(path.c_str(), &st) == 0;
@@ -428,11 +441,19 @@ int fi_learner_forward_backward(fi_learner* l, int player, const fi_batch* b) {
         FI_CUDA_OK(cudaEventRecord(p->batch_ready, (cudaStream_t)b->stream));
         FI_CUDA_OK(cudaStreamWaitEvent(p->stream, p->batch_ready, 0));
     }
-    const int m = (int)b->num_slots, t = (int)l->cfg.entry_size, global_m = m * l->dp_world;
+    const int m = (int)b->num_slots, t = (int)l->cfg.entry_size;
+    // mean losses divide by the GLOBAL batch: under data parallelism that is the sum of the ranks' configured batch sizes
+    // (all-reduced once in fi_learner_dp_init; shards may differ by one trajectory), so every rank must step full batches
+    if (l->dp_world > 1 && (size_t)m != l->cfg.batch_size)
+        return set_error(FI_ERR_STATE, "fi_learner_forward_backward: a partial batch (%d of %zu trajectories) cannot be combined with "
+                                       "data parallelism (the global batch size is fixed at fi_learner_dp_init)", m, l->cfg.batch_size);
+    const int global_m = l->dp_world > 1 ? (int)l->dp_global_batch : m;
     if (l->cfg.model == FI_MODEL_FARMER_LSTM) FI_TRY(fi::farmer_forward_backward(l, p, (const float*)b->dev_ptr, m, t, global_m));
     else FI_TRY(fi::ac_forward_backward(l, p, (const float*)b->dev_ptr, m, t, global_m));
     p->last_rows = (size_t)m * t;
     p->grads_valid = true;
+    // the batch buffer may be rewritten by its ring's next gather once everything enqueued above has read it
+    FI_TRY(fi::ring_note_consumed(b->dev_ptr, p->stream));
     return FI_OK;
 }
 
@@ -455,17 +476,18 @@ int fi_learner_apply_update(fi_learner* l, int player) {
         ls.done_external();
     }
     p->opt_step++;
-    p->steps_done++;
+    const uint64_t steps_done = p->steps_done.load(std::memory_order_relaxed) + 1;
     p->version++;  // generateRandomData(): version++ (data_structures.h:121-127), then updateModel
-    const bool publish = p->steps_done % (uint64_t)l->cfg.publish_every == 0;
+    const bool publish = steps_done % (uint64_t)l->cfg.publish_every == 0;
     int sn = -1;
     if (publish) FI_TRY(publish_begin(p, &sn));
     // one kernel: the update, the model store's device snapshot and the loss read-back (into mapped pinned memory)
-    const int slot = (int)(p->steps_done % Player::kLossRing);
+    const int slot = (int)(steps_done % Player::kLossRing);
     FI_TRY(fi::launch_opt(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m,
                           p->adam_v, 1.0f, p->stream, publish ? p->store.dev_snap[sn] : nullptr, p->d_losses,
                           p->h_losses_dev + 4 * slot));
     FI_CUDA_OK(cudaEventRecord(p->loss_ev[slot], p->stream));
+    p->steps_done.store(steps_done, std::memory_order_release);   // readers (losses_at, steps_done) see the event recorded
     if (publish) FI_TRY(publish_end(p, p->version, sn));
     return FI_OK;
 }
@@ -479,8 +501,9 @@ int fi_learner_last_losses(fi_learner* l, int player, float losses[4]) {
     Player* p = get_player(l, player);
     if (!p || !losses) return set_error(FI_ERR_ARG, "fi_learner_last_losses: null argument");
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
-    const int slot = (int)(p->steps_done % Player::kLossRing);
-    if (p->steps_done == 0 && p->grads_valid) {  // forward_backward only: read straight from the device
+    const uint64_t done = p->steps_done.load(std::memory_order_acquire);
+    const int slot = (int)(done % Player::kLossRing);
+    if (done == 0 && p->grads_valid) {  // forward_backward only: read straight from the device
         FI_CUDA_OK(cudaMemcpyAsync(p->h_losses, p->d_losses, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         FI_CUDA_OK(cudaEventRecord(p->loss_ev[0], p->stream));
     }
@@ -491,9 +514,10 @@ int fi_learner_last_losses(fi_learner* l, int player, float losses[4]) {
 int fi_learner_losses_at(fi_learner* l, int player, uint64_t step, float losses[4]) {
     Player* p = get_player(l, player);
     if (!p || !losses) return set_error(FI_ERR_ARG, "fi_learner_losses_at: null argument");
-    if (step == 0 || step > p->steps_done || step + Player::kLossRing <= p->steps_done)
+    const uint64_t done = p->steps_done.load(std::memory_order_acquire);   // the worker thread increments it under step_mu
+    if (step == 0 || step > done || step + Player::kLossRing <= done)
         return set_error(FI_ERR_ARG, "fi_learner_losses_at: step %llu is not among the last %d of %llu", (unsigned long long)step,
-                         Player::kLossRing, (unsigned long long)p->steps_done);
+                         Player::kLossRing, (unsigned long long)done);
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
     const int slot = (int)(step % Player::kLossRing);
     FI_CUDA_OK(cudaEventSynchronize(p->loss_ev[slot]));
@@ -511,7 +535,7 @@ int fi_learner_last_losses_f64(fi_learner* l, int player, double losses[4]) {
 }
 uint64_t fi_learner_steps_done(fi_learner* l, int player) {
     Player* p = get_player(l, player);
-    return p ? p->steps_done : 0;
+    return p ? p->steps_done.load(std::memory_order_acquire) : 0;
 }
 
 size_t fi_learner_param_count(const fi_learner* l) { return l ? l->param_count : 0; }
@@ -684,10 +708,16 @@ int fi_model_save(fi_learner* l, int player, uint64_t iteration, int with_optimi
         std::lock_guard<std::mutex> g(s.mu);
         stamp = p->checkpoint_counter++;
     }
-    mkdir(l->ckpt_dir.c_str(), 0777);
+    // create_directories (data_structures.h:94-97): every missing component of the path
+    if (!make_dirs(l->ckpt_dir)) return set_error(FI_ERR_IO, "fi_model_save: cannot create directory %s", l->ckpt_dir.c_str());
     const std::string base = l->ckpt_dir + "/model_" + std::to_string(player) + "_";
     const std::string paths[2] = {base + std::to_string(stamp) + ".bin", base + "latest.bin"};
-    for (const std::string& path : paths) {
+    // One save per player at a time, and every file appears under its final name only when it is complete (written to a
+    // temporary name in the same directory, then rename()d): a checkpoint thread and the final save of stop() can no
+    // longer interleave their writes into one latest.bin.
+    std::lock_guard<std::mutex> save_lock(p->save_mu);
+    for (const std::string& final_path : paths) {
+        const std::string path = final_path + ".tmp";
         FILE* f = fopen(path.c_str(), "wb");
         if (!f) return set_error(FI_ERR_IO, "fi_model_save: cannot open %s", path.c_str());
         bool ok = fwrite(&version, sizeof(version), 1, f) == 1 && fwrite(blob.data(), 1, blob.size(), f) == blob.size();
@@ -697,7 +727,12 @@ int fi_model_save(fi_learner* l, int player, uint64_t iteration, int with_optimi
                  fwrite(om.data(), 4, n, f) == n && fwrite(ov.data(), 4, n, f) == n;
         }
         ok = (fclose(f) == 0) && ok;
-        if (!ok) return set_error(FI_ERR_IO, "fi_model_save: short write to %s", path.c_str());
+        if (!ok) {
+            remove(path.c_str());
+            return set_error(FI_ERR_IO, "fi_model_save: short write to %s", path.c_str());
+        }
+        if (rename(path.c_str(), final_path.c_str()) != 0)
+            return set_error(FI_ERR_IO, "fi_model_save: cannot rename %s to %s", path.c_str(), final_path.c_str());
     }
     return FI_OK;
 }
@@ -795,6 +830,21 @@ int fi_learner_dp_init(fi_learner* l, const void* ids, int rank, int world_size)
     }
     l->dp_rank = rank;
     l->dp_world = world_size;
+    // the global batch = sum of the ranks' batch sizes (shards of a global batch may differ by one: dp.shard_range)
+    l->dp_global_batch = l->cfg.batch_size * (size_t)world_size;
+    if (world_size > 1) {
+        Player* p0 = l->players[0];
+        double* d = nullptr;
+        FI_CUDA_OK(cudaMalloc((void**)&d, sizeof(double)));
+        const double mine = (double)l->cfg.batch_size;
+        FI_CUDA_OK(cudaMemcpyAsync(d, &mine, sizeof(double), cudaMemcpyHostToDevice, p0->stream));
+        FI_NCCL_OK(nccl().AllReduce(d, d, 1, ncclDouble, ncclSum, (ncclComm_t)p0->nccl_comm, p0->stream));
+        double total = 0.0;
+        FI_CUDA_OK(cudaMemcpyAsync(&total, d, sizeof(double), cudaMemcpyDeviceToHost, p0->stream));
+        FI_CUDA_OK(cudaStreamSynchronize(p0->stream));
+        cudaFree(d);
+        l->dp_global_batch = (size_t)(total + 0.5);
+    }
     return FI_OK;
 }
 int fi_learner_dp_world(const fi_learner* l) { return l ? l->dp_world : 0; }

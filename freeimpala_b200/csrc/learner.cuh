@@ -62,7 +62,7 @@ struct Player {
     cudaStream_t stream = nullptr;
     float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
     int64_t opt_step = 0;
-    uint64_t steps_done = 0;
+    std::atomic<uint64_t> steps_done{0};  // written under step_mu (release), read without it by fi_learner_losses_at / steps_done
     uint64_t version = 1;       // version of the weights in `params` (Model ctor -> 1, :55-58,127)
     double* d_losses = nullptr; // device double[4]
     // loss read-back ring: step s (1-based) lands in slot s % kLossRing of the pinned array, so that a host loop can read
@@ -96,6 +96,7 @@ struct Player {
     size_t inf_rows_cap = 0, inf_t_cap = 0;
     ModelStore store;
     uint64_t checkpoint_counter = 0;
+    std::mutex save_mu;         // one fi_model_save per player at a time
     void* nccl_comm = nullptr;  // one communicator per player: players step concurrently
 };
 
@@ -109,6 +110,7 @@ struct fi_learner {
     std::vector<fi_ring*> rings;
     std::vector<fi::Player*> players;
     int dp_rank = 0, dp_world = 1;
+    size_t dp_global_batch = 0;  // sum of the ranks' batch sizes (fi_learner_dp_init)
 };
 
 namespace fi {

@@ -5,6 +5,7 @@
 // (INTEGRATION.md shows the two-line switch). Header-only, like the reference; no CUDA or torch types.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <memory>
@@ -84,16 +85,45 @@ public:
     bool waitForModelUpdate(size_t p, uint64_t current_version, int timeout_ms) {                                    // :454-472
         return p < players_ && fi_model_wait_update(l_, (int)p, current_version, timeout_ms) == 1;
     }
-    void saveModel(size_t p, uint64_t current_iteration = 0) {                                                       // :388-423
-        if (p < players_) fi_model_save(l_, (int)p, current_iteration, /*with_optimizer_state=*/1);
+    // File = u64 version + raw parameter bytes, exactly the reference's size and layout (:105-110). setSaveOptimizerState(true)
+    // appends the Adam moments + step in a trailing section old readers ignore (exact resume; 3x the file size): opt-in.
+    // Returns false (and the library has logged why) when the file could not be written; the reference's saveModel is
+    // void and logs, so existing callers keep compiling.
+    bool saveModel(size_t p, uint64_t current_iteration = 0) {                                                       // :388-423
+        if (p >= players_) return false;
+        const bool ok = fi_model_save(l_, (int)p, current_iteration, save_optimizer_state_ ? 1 : 0) == FI_OK;
+        if (!ok) std::fprintf(stderr, "[fi_host][error] saveModel(player %zu, iteration %llu) failed: %s\n", p,
+                              (unsigned long long)current_iteration, fi_last_error());
+        return ok;
     }
-    void saveAllModels(uint64_t current_iteration = 0) { for (size_t p = 0; p < players_; p++) saveModel(p, current_iteration); }
+    bool saveAllModels(uint64_t current_iteration = 0) {
+        bool ok = true;
+        for (size_t p = 0; p < players_; p++) ok = saveModel(p, current_iteration) && ok;
+        return ok;
+    }
+    void setSaveOptimizerState(bool on) { save_optimizer_state_ = on; }
     void loadModels(const std::string& path) { if (!path.empty()) fi_model_load(l_, path.c_str()); }                 // :337-385
 
 private:
     fi_learner* l_;
     size_t players_;
+    bool save_optimizer_state_ = false;
 };
+
+// The two MetricsTracker calls the reference's trainModel makes (learner.h:34 createTrainingTimer, :48
+// recordLearnerModelUpdate) are kept at the same two points of the step. In the integrated build FI_HOST_METRICS_TRACKER is
+// defined before this header is included and they go to the reference's own singleton
+// (include/freeimpala/metrics_tracker.h:147-177, 213-217); stand-alone (tests, the harness) they feed the counters below.
+struct StepMetrics {
+    std::atomic<uint64_t> model_updates{0}, training_ns{0};
+};
+#ifdef FI_HOST_METRICS_TRACKER
+#define FI_HOST_TRAINING_TIMER() auto fi_host_training_timer = MetricsTracker::getInstance()->createTrainingTimer()
+#define FI_HOST_RECORD_MODEL_UPDATE() MetricsTracker::getInstance()->recordLearnerModelUpdate()
+#else
+#define FI_HOST_TRAINING_TIMER() (void)0
+#define FI_HOST_RECORD_MODEL_UPDATE() (void)0
+#endif
 
 class Learner {
 public:
@@ -132,15 +162,21 @@ public:
         for (auto& t : worker_threads_) if (t.joinable()) t.join();
         worker_threads_.clear();
         for (size_t p = 0; p < num_players_; p++) fi_learner_sync(h_, (int)p);
+        {
+            // in-progress checkpoint threads finish BEFORE the final save (the reference saves first and joins after,
+            // learner.h:184-196; with real files two writers of model_p_latest.bin must not overlap -- the library also
+            // serialises saves per player and renames complete files into place)
+            std::lock_guard<std::mutex> lock(checkpoint_mutex_);
+            for (auto& t : checkpoint_threads_) if (t.joinable()) t.join();
+            checkpoint_threads_.clear();
+        }
         if (!checkpoint_location_.empty()) model_manager_->saveAllModels(total_iterations_);
-        std::lock_guard<std::mutex> lock(checkpoint_mutex_);
-        for (auto& t : checkpoint_threads_) if (t.joinable()) t.join();
-        checkpoint_threads_.clear();
     }
     std::vector<std::shared_ptr<SharedBuffer>> getSharedBuffers() { return shared_buffers_; }   // learner.h:200-202
     std::shared_ptr<ModelManager> getModelManager() { return model_manager_; }                   // learner.h:205-207
     fi_learner* handle() const { return h_; }
     size_t iterationsDone(size_t p) const { return iterations_[p]; }
+    const StepMetrics& stepMetrics() const { return metrics_; }   // model updates / host time inside trainModel (stand-alone counters)
     // Losses of player p's optimiser step `step` (1-based, one of the last 8): {total, pg, baseline, entropy} for V-trace,
     // {loss,0,0,0} for the regression step. Waits only for that step's read-back (no counterpart in the reference, whose
     // trainModel computes nothing to log).
@@ -148,9 +184,23 @@ public:
 
 private:
     void trainModel(size_t p, const DeviceBatch& batch) {                      // learner.h:32-49
-        // the reference wraps this in MetricsTracker::createTrainingTimer() and calls
-        // recordLearnerModelUpdate(); the integrated build keeps both calls
-        if (fi_learner_step(h_, (int)p, &batch.raw) != FI_OK) should_stop_.store(true);  // logged; reference style: no throw
+        FI_HOST_TRAINING_TIMER();                                              // learner.h:33-34
+        const auto t0 = std::chrono::steady_clock::now();
+        // forward, loss, backward, (all-reduce), Adam and the publication of version + 1, all enqueued on the player's stream
+        if (fi_learner_step(h_, (int)p, &batch.raw) != FI_OK) {                // logged by the library; reference style: no throw
+            should_stop_.store(true);
+            return;
+        }
+        metrics_.training_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                           std::chrono::steady_clock::now() - t0).count());
+        metrics_.model_updates.fetch_add(1);
+        FI_HOST_RECORD_MODEL_UPDATE();                                         // learner.h:47-48
+    }
+    void checkpointModel(size_t p, uint64_t it) {                              // learner.h:52-69
+        std::lock_guard<std::mutex> lock(checkpoint_mutex_);
+        for (auto& t : checkpoint_threads_) if (t.joinable()) t.join();       // reap finished checkpoint threads (:56-63)
+        checkpoint_threads_.clear();
+        checkpoint_threads_.emplace_back([this, p, it] { model_manager_->saveModel(p, it); });
     }
     void workerThread(size_t p) {                                              // learner.h:72-97
         size_t it = 0;
@@ -163,10 +213,7 @@ private:
             }
             trainModel(p, batch);
             iterations_[p] = ++it;
-            if (checkpoint_frequency_ > 0 && it % checkpoint_frequency_ == 0 && !checkpoint_location_.empty()) {
-                std::lock_guard<std::mutex> lock(checkpoint_mutex_);
-                checkpoint_threads_.emplace_back([this, p, it] { model_manager_->saveModel(p, it); });
-            }
+            if (checkpoint_frequency_ > 0 && it % checkpoint_frequency_ == 0 && !checkpoint_location_.empty()) checkpointModel(p, it);
         }
     }
 
@@ -180,6 +227,7 @@ private:
     std::vector<size_t> iterations_;
     std::atomic<bool> should_stop_{false}, stopped_{false};
     std::mutex checkpoint_mutex_;
+    StepMetrics metrics_;
 };
 
 }  // namespace fi_host

@@ -105,6 +105,7 @@ class Learner:
         self.should_stop = threading.Event()
         self.worker_threads: list[threading.Thread] = []
         self.checkpoint_threads: list[threading.Thread] = []
+        self._checkpoint_lock = threading.Lock()
         self.iterations_done = [0] * p
         self.errors: list[str] = []
 
@@ -132,11 +133,12 @@ class Learner:
         self.worker_threads.clear()
         for p in range(self.num_players):
             self.sync(p)
+        with self._checkpoint_lock:   # in-progress checkpoints finish before the final save (one writer per file)
+            for t in self.checkpoint_threads:
+                t.join()
+            self.checkpoint_threads.clear()
         if self.checkpoint_location:
             self.model_manager.saveAllModels(self.total_iterations)
-        for t in self.checkpoint_threads:
-            t.join()
-        self.checkpoint_threads.clear()
 
     def close(self) -> None:
         if self._h is not None:
@@ -170,9 +172,22 @@ class Learner:
             it += 1
             self.iterations_done[p] = it
             if self.checkpoint_frequency > 0 and it % self.checkpoint_frequency == 0 and self.checkpoint_location:
-                t = threading.Thread(target=self.model_manager.saveModel, args=(p, it))
-                self.checkpoint_threads.append(t)
-                t.start()
+                self._checkpoint_model(p, it)
+
+    def _checkpoint_model(self, p: int, it: int) -> None:  # learner.h:52-69: reap finished checkpoint threads, start one
+        with self._checkpoint_lock:
+            for t in self.checkpoint_threads:
+                t.join()
+            self.checkpoint_threads.clear()
+            t = threading.Thread(target=self._save_logged, args=(p, it))
+            self.checkpoint_threads.append(t)
+            t.start()
+
+    def _save_logged(self, p: int, it: int) -> None:
+        try:
+            self.model_manager.saveModel(p, it)
+        except _lib.FiError as e:   # the reference logs a failed save and carries on
+            self.errors.append(str(e))
 
     def trainModel(self, player_index: int, batch: Batch) -> None:  # learner.h:32-49
         check(self._lib.fi_learner_step(self._h, player_index, C.byref(batch.raw)), "fi_learner_step")

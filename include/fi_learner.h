@@ -57,6 +57,10 @@ typedef struct fi_prof_entry {
 } fi_prof_entry;
 FI_API void fi_prof_enable(int on);
 FI_API int fi_prof_collect(fi_prof_entry* out, int max_entries);
+/* Diagnostics (tools/gemm_trace.py): with FI_TC_TRACE="<trans>,<min n>,<min k>" in the environment, matching tcgen05 GEMM
+ * launches log the pipeline events of their first 4 CTAs; this copies the last log out. Layout [cta 0..3][role 0..2][4096]
+ * of (clock64 << 8 | tag), 0 = unused. Returns the number of 8-byte entries or a negative fi_status. No reference counterpart. */
+FI_API int fi_debug_tc_trace(void* host, size_t bytes);
 
 /* ============================ trajectory ring ============================================
  * Replaces SharedBuffer (include/freeimpala/data_structures.h:191-307). One ring per
