@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--workload", default="vtrace", choices=["vtrace", "farmer"],
                     help="vtrace: MLP actor-critic V-trace step (headline); farmer: the reference's FarmerLstm/MSE/Adam step")
     ap.add_argument("--writers", type=int, default=0, help="actor threads feeding the ring in the e2e leg (0: min(16, host cores / ranks))")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch trajectories per GPU (default); strong: --batch is the GLOBAL batch, sharded over the ranks")
+    ap.add_argument("--no-reference-workload", action="store_true", help="skip the FarmerLstm leg of the default (V-trace) run")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg of a multi-GPU weak-scaling run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
@@ -142,8 +146,8 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------
 def cpu_baseline_port(seq: int, budget_s: float):
-    """The oracle's float64 restatement of the SAME workload (V-trace actor-critic step) on the
-    host cores: a bounded sample of 8-trajectory steps. kind = "port"."""
+    """The oracle's float64 restatement of the V-trace actor-critic step on the host cores: a bounded sample of
+    8-trajectory steps (kind "port"). Reported beside the reference figure; the reference has no V-trace step."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import pyoracle as po
     o = po.Oracle()
@@ -166,13 +170,22 @@ def cpu_baseline_port(seq: int, budget_s: float):
             "sample": f"{n} V-trace actor-critic steps of {m} x {seq} transitions (float64 C port, OpenMP), {dt:.1f} s"}
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_libtorch(batch: int, seq: int, warmup: int, steps: int):
-    """The reference's own learner math: cmd/libtorch_bench train_step (FarmerLstm, MSE, Adam lr 5e-4)
-    compiled from the reference's sources into oracle/_ref, on the host cores."""
+    """The reference's own learner math: cmd/libtorch_bench train_step (FarmerLstm, MSE, Adam lr 5e-4) compiled from the
+    reference's sources into oracle/_ref, on ALL the host cores this process may use (torchrun exports OMP_NUM_THREADS=1
+    to its workers: the thread count is set explicitly, VERDICT r1 weak #11)."""
     from oracle import pyoracle as po
     if not os.path.exists(po.REF_NN_SO):
         return None
     r = po.RefNN(seed=1, opt="adam", lr=5e-4, loss="mse")
+    r.lib.ref_nn_set_num_threads(host_cores())
     ms = r.bench(batch, seq, warmup, steps)
     return {"ms_per_step": ms, "value": batch * seq / (ms / 1e3), "cores": r.num_threads}
 
@@ -185,6 +198,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())   # before libtorch's OpenMP runtime starts
     cfg = {"workload": f"learner step, batch {args.batch} x T={args.seq} (reference arm: libtorch_bench FarmerLstm "
                        f"MSE/Adam train_step on CPU; the reference has no V-trace)",
            "batch_per_gpu": args.batch, "seq_len": args.seq}
@@ -206,57 +220,66 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
-def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
+class Job:
+    """Process-wide state of the b200 arm: rank / world, torch, barriers, reductions over ranks."""
 
-    import freeimpala_b200 as fi
-    from freeimpala_b200._lib import FiBatch
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            if self.world == 1 and args.gpus > 1:  # convenience: relaunch under torchrun
+                cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                       "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), *sys.argv]
+                sys.exit(subprocess.call(cmd))
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:  # convenience: relaunch under torchrun
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), *sys.argv]
-            sys.exit(subprocess.call(cmd))
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def all_ranks(x: float) -> list:
-        if world == 1:
+    def all_ranks(self, x: float) -> list:
+        if self.world == 1:
             return [x]
-        t = torch.zeros(world, dtype=torch.float64, device="cuda")
-        t[rank] = x
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = x
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    M, T = args.batch, args.seq
+
+def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: bool, with_prof: bool):
+    """One workload at M trajectories per GPU: `value` (inputs resident in HBM, EXACTLY K steps between two events on the
+    learner's stream, max over ranks), the per-kernel profile of a second, instrumented pass, and `e2e` (host buffers through
+    SharedBuffer::write -> readBatch -> trainModel -> loss read-back, wall clock, max over ranks)."""
+    import freeimpala_b200 as fi
+    from freeimpala_b200 import dp
+    from freeimpala_b200._lib import FiBatch
+    torch = job.torch
+    rank, world, local = job.rank, job.world, job.local
+    T = args.seq
     slot_bytes = T * 1024
-    K, W = args.steps, max(args.warmup, 0)
+    K, W = args.steps, max(args.warmup, 3)
     cap = 2 * M
-    farmer = args.workload == "farmer"
+    farmer = workload == "farmer"
     ring_cap = 4 * M   # learner's pinned-host/HBM ring: producers may run up to three batches ahead of the learner
     L = fi.Learner(1, ring_cap, T, M, model="farmer_lstm" if farmer else "mlp_actor_critic", device=local,
                    gemm_mode=args.gemm_mode, seed=1, lr=5e-4, publish_every=args.publish_every)
-    from freeimpala_b200 import dp
     dp.init_learner_dp(L, rank, world)
     lib = fi.load_library()
     stream_ptr = lib.fi_learner_stream(L._h, 0)
@@ -278,22 +301,17 @@ def run_b200_arm(args):
         raw = FiBatch(batch_dev.data_ptr(), M, slot_bytes, stream_ptr, 0)
         L.trainModel(0, fi.Batch(raw))
 
-    sampler = ClockSampler(range(world))   # rank 0 samples every GPU of the job: the slowest one sets the step time
-    windows = []
-    if rank == 0:
-        sampler.start()
-
     # ---------------- value: inputs resident in HBM -------------------------------------------
-    for i in range(max(W, 3)):
+    for i in range(W):
         device_step(i)
     L.sync(0)
-    barrier()
+    job.barrier()
     torch.cuda.synchronize()
     per_rank_ms = []   # [pass][rank]: every rank's own device time per step (the headline is the max)
 
     def timed_pass(profiled: bool):
         L.sync(0)
-        barrier()
+        job.barrier()
         torch.cuda.synchronize()
         fi.prof_collect()
         fi.prof_enable(profiled)
@@ -306,41 +324,41 @@ def run_b200_arm(args):
         ev1.record(ext)
         L.sync(0)
         torch.cuda.synchronize()
-        barrier()
+        job.barrier()
         windows.append((w0, time.time()))
         fi.prof_enable(False)
-        per_rank_ms.append(all_ranks(ev0.elapsed_time(ev1) / K))
+        per_rank_ms.append(job.all_ranks(ev0.elapsed_time(ev1) / K))
         return max(per_rank_ms[-1]) * K, fi.kernel_launch_count() - n0, fi.prof_collect()
 
     # Pass 1 is the headline: EXACTLY K steps, two events on the learner's stream, no instrumentation in between.
     # Pass 2 repeats the same K steps with every launch bracketed by its own event pair (fi_prof_enable) for the per-kernel
-    # rooflines; the ~80 extra event records per step cost about 10 % of a step (tools/host_enqueue.py), which is why the
+    # rooflines; the extra event records per step cost about 10 % of a step (tools/host_enqueue.py), which is why the
     # headline does not come from the instrumented pass. Kernel shares are quoted against pass 2's own step time.
     ms_total, launches, _ = timed_pass(False)
-    ms_prof_total, _, prof = timed_pass(True)
-    ms_per_step_prof = ms_prof_total / K
-    losses = L.last_losses(0)
-    ms_per_step = ms_total / K
-    value = world * M * T / (ms_per_step / 1e3)
+    res = {"M": M, "ms_per_step": ms_total / K, "value": world * M * T / (ms_total / K / 1e3), "launches": int(launches),
+           "per_rank_ms": per_rank_ms[0], "param_count": L.param_count, "ring_cap": ring_cap, "prof": None, "e2e": None}
+    if with_prof:
+        ms_prof_total, _, prof = timed_pass(True)
+        res["prof"], res["ms_per_step_prof"] = prof, ms_prof_total / K
+    res["losses"] = [float(x) for x in L.last_losses(0)]
 
     # ---------------- e2e: host buffers through SharedBuffer.write -> trainModel -> loss read-back ---
-    e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         ring = L.getSharedBuffers()[0]
-        cores_per_rank = max(1, (os.cpu_count() or 8) // world)
-        nw_copy = args.writers if args.writers > 0 else max(2, min(16, cores_per_rank))
+        cores_per_rank = max(1, host_cores() // world)
+        nw_copy = args.writers if args.writers > 0 else max(2, min(8, cores_per_rank - 1))
         nw_zc = int(os.environ.get("FI_BENCH_ZC_THREADS", "2"))  # in-place producers only take the ring lock: two threads keep the ring full
         zc_burst = int(os.environ.get("FI_BENCH_ZC_BURST", "64"))
 
         def copy_writer(j: int, steps: int, nw: int):
             # actor thread j owns trajectories [j*per, (j+1)*per) of every step: SharedBuffer::write semantics (the ring
-            # copies the caller's bytes into the pinned slot), handed over in bursts of 16
+            # copies EVERY byte of the caller's trajectory into the pinned slot), handed over in bursts of 32
             per = (M + nw - 1) // nw
             for s in range(steps):
                 base = (s % 2) * M
                 lo, hi = j * per, min(M, (j + 1) * per)
-                for i in range(lo, hi, 16):
-                    ring.write_many(host[base + i:base + min(i + 16, hi)])
+                for i in range(lo, hi, 32):
+                    ring.write_many(host[base + i:base + min(i + 32, hi)])
 
         def inplace_writer(j: int, steps: int, nw: int):
             # zero-copy producer (fi_ring_reserve_many / fi_ring_commit_many): the trajectory is produced IN the pinned slot
@@ -381,40 +399,43 @@ def run_b200_arm(args):
 
         def timed(writer, nw):
             L.sync(0)
-            barrier()
+            job.barrier()
             torch.cuda.synchronize()
             t0, tw0 = time.perf_counter(), time.time()
             e2e_steps(K, writer, nw)
             L.sync(0)
             torch.cuda.synchronize()
             t1, tw1 = time.perf_counter(), time.time()
-            barrier()
+            job.barrier()
             windows.append((tw0, tw1))
-            return max_over_ranks(t1 - t0)
+            return job.max_over_ranks(t1 - t0)
 
-        e2e_steps(max(W, 4), copy_writer, nw_copy)   # warm-up; also leaves a valid trajectory in each of the 2M pinned slots
+        e2e_steps(max(W, 4), copy_writer, nw_copy)   # warm-up; also leaves a valid trajectory in each pinned slot
         host_ms.update(readBatch=0.0, trainModel=0.0)
-        zc_s = timed(inplace_writer, nw_zc)
-        zc_host = {k: v / K for k, v in host_ms.items()}   # rank 0's host time per step inside the two calls (blocking included)
         copy_s = timed(copy_writer, nw_copy)
-        e2e = {"value": world * M * T * K / zc_s, "unit": UNIT, "ms_per_step": zc_s / K * 1e3,
-               "h2d_bytes_per_step": world * M * slot_bytes,
-               "d2h_bytes_per_step": world * (32 + 4 * L.param_count),
-               "path": f"trajectories produced in place in the ring's pinned slots (fi_ring_reserve_many / fi_ring_commit_many, "
-                       f"{nw_zc} producer threads) -> cudaMemcpyAsync per run of slots on the side stream -> readBatch (gather "
-                       f"kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H every step; the loss of step s is read by the host while step s+1 runs (fi_learner_losses_at)",
-               "losses_read": len(e2e_losses), "host_ms_per_step": zc_host,
-               "write_copy": {"value": world * M * T * K / copy_s, "ms_per_step": copy_s / K * 1e3, "actor_threads": nw_copy,
-                              "host_cores_per_rank": cores_per_rank,
-                              "path": "same, but through SharedBuffer::write semantics (fi_ring_write_many): every trajectory is "
-                                      "first copied from the actor's buffer into the pinned slot by the host"}}
+        copy_host = {k: v / K for k, v in host_ms.items()}   # rank 0's host time per step inside the two calls (blocking included)
+        zc_s = timed(inplace_writer, nw_zc)
+        res["e2e"] = {
+            "value": world * M * T * K / copy_s, "unit": UNIT, "ms_per_step": copy_s / K * 1e3,
+            "h2d_bytes_per_step": world * M * slot_bytes, "d2h_bytes_per_step": world * (32 + 4 * L.param_count),
+            "actor_threads": nw_copy, "host_cores_per_rank": cores_per_rank,
+            "path": f"{nw_copy} actor threads per rank call SharedBuffer::write semantics (fi_ring_write_many: every byte of every "
+                    f"trajectory is copied from the actor's buffer into a pinned ring slot) -> cudaMemcpyAsync per run of slots on the "
+                    f"side stream -> readBatch (gather kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H "
+                    f"every step; the loss of step s is read by the host while step s+1 runs (fi_learner_losses_at)",
+            "losses_read": len(e2e_losses), "host_ms_per_step": copy_host,
+            "inplace": {"value": world * M * T * K / zc_s, "ms_per_step": zc_s / K * 1e3, "producer_threads": nw_zc,
+                        "path": "zero-copy producer API (fi_ring_reserve_many / fi_ring_commit_many): the trajectory already sits in the "
+                                "pinned slot (an MPI_Irecv posted into it); the producer only stamps one word per burst, so this leg "
+                                "measures the ring + H2D + step without the host memcpy"}}
+    L.close()
+    lib.fi_host_free(host_ptr)
+    return res
 
-    clocks = sampler.stop(windows) if rank == 0 else None
 
-    # ---------------- per-kernel roofline from the timed region --------------------------------------
-    peaks = measured_peaks()
+def kernel_table(prof, K, ms_per_step_prof, world, peaks):
     kernels = {}
-    for name, r in prof.items():
+    for name, r in (prof or {}).items():
         if r["launches"] == 0 or r["total_ms"] <= 0:
             continue
         avg_ms = r["total_ms"] / r["launches"]
@@ -428,20 +449,52 @@ def run_b200_arm(args):
         kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                          "launches_per_step": r["launches"] / K, "avg_us": avg_ms * 1e3,
                          "share_of_step": r["total_ms"] / (ms_per_step_prof * K) if world == 1 else None}
+    return kernels
+
+
+def run_b200_arm(args):
+    job = Job(args)
+    rank, world = job.rank, job.world
+    T, K = args.seq, args.steps
+    farmer = args.workload == "farmer"
+    strong = args.scaling == "strong"
+    if strong and args.batch % world:
+        raise SystemExit(f"--scaling strong needs --batch {args.batch} divisible by the {world} ranks")
+    M = args.batch // world if strong else args.batch
+
+    sampler = ClockSampler(range(world))   # rank 0 samples every GPU of the job: the slowest one sets the step time
+    windows = []
+    if rank == 0:
+        sampler.start()
+    main = measure(job, args, args.workload, M, windows, with_e2e=not args.no_e2e, with_prof=True)
+    # the reference's own learner step (FarmerLstm / MSE / Adam) at the same batch x seq, in the same run: the like-for-like
+    # partner of `bench.py --impl reference` (the headline V-trace step has no counterpart in the reference)
+    ref_wl = None
+    if not farmer and not args.no_reference_workload:
+        ref_wl = measure(job, args, "farmer", M, windows, with_e2e=not args.no_e2e, with_prof=False)
+    # strong scaling (batch 1024 GLOBAL, sharded M/N per GPU) beside the weak-scaling headline
+    strong_wl = None
+    if world > 1 and not strong and not farmer and args.batch % world == 0 and not args.no_strong:
+        strong_wl = measure(job, args, args.workload, args.batch // world, windows, with_e2e=False, with_prof=False)
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    ms_per_step, value, launches = main["ms_per_step"], main["value"], main["launches"]
+    peaks = measured_peaks()
+    kernels = kernel_table(main["prof"], K, main["ms_per_step_prof"], world, peaks)
     own = [k for k in kernels if not k.startswith("nccl_")]   # the all-reduce entry is skew + transfer, not one of our kernels
-    dominant = max(own, key=lambda k: prof[k]["total_ms"]) if own else None
+    dominant = max(own, key=lambda k: main["prof"][k]["total_ms"]) if own else None
     roofline = None
     if dominant:
         d = kernels[dominant]
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
         traffic, traffic_src = None, None
-        prof_name = "r1_gemm_f16x3" if "f16x3" in dominant else "r1_gemm_tc"
-        tpath = os.path.join(ROOT, "profiles", prof_name + "_traffic.json")
-        if os.path.exists(tpath) and not farmer:
-            tj = json.load(open(tpath))
-            key = next((k for k in tj if k.startswith(dominant) and "BN=128" in k), None)
-            if key:
-                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], f"profiles/{prof_name}.md ({key}, big-layer launches)"
+        for prof_name in ("r2_gemm_traffic", "r1_gemm_f16x3_traffic"):
+            tpath = os.path.join(ROOT, "profiles", prof_name + ".json")
+            if traffic is None and os.path.exists(tpath) and not farmer:
+                tj = json.load(open(tpath))
+                key = next((k for k in tj if k.startswith(dominant.split(">")[0].rsplit(",", 1)[0] if dominant.count(",") > 1 else dominant)), None)
+                if key:
+                    traffic, traffic_src = tj[key]["dram_bytes_per_launch"], f"profiles/{prof_name}.json ({key})"
         roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
                     "note": ("tensor peak = cuBLAS bf16 sustained; `achieved` counts the 2mnk algorithmic flops, and every "
@@ -454,36 +507,49 @@ def run_b200_arm(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_port(T, args.cpu_seconds)
+        # the reference's own CPU learner step (libtorch_bench train_step, FarmerLstm/MSE/Adam) at this batch x seq on the box's
+        # host cores: a bounded sample (~0.15 s per step on 16 cores); falls back to the oracle's port if oracle/_ref is absent
         try:
-            ref = reference_libtorch(64, T, 2, 5)
-            if ref:
-                cpu["reference_libtorch_farmer_b64"] = {"value": ref["value"], "unit": UNIT, "cores": ref["cores"],
-                                                        "ms_per_step": ref["ms_per_step"],
-                                                        "sample": "libtorch_bench train_step, batch 64 x seq 100 (README shape)"}
+            n_ref = max(3, min(20, int(args.cpu_seconds / 0.4)))
+            ref = reference_libtorch(args.batch, T, 2, n_ref)
         except Exception as e:  # the reference build is optional on the GPU box
-            cpu["reference_libtorch_farmer_b64"] = {"unavailable": str(e)[:200]}
+            ref = None
+            sys.stderr.write(f"cpu_baseline: reference libtorch step unavailable: {e}\n")
+        if ref:
+            cpu = {"value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "reference",
+                   "ms_per_step": ref["ms_per_step"],
+                   "sample": f"{n_ref} libtorch_bench train_step calls (FarmerLstm, MSE, Adam) at batch {args.batch} x seq {T} after 2 warm-ups; "
+                             f"the reference has no V-trace step: compare with reference_workload"}
+            cpu["vtrace_port"] = cpu_baseline_port(T, min(args.cpu_seconds, 4.0))
+        else:
+            cpu = cpu_baseline_port(T, args.cpu_seconds)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        def wl_block(w, name):
+            return None if w is None else {
+                "workload": name, "value": w["value"], "unit": UNIT, "ms_per_step": w["ms_per_step"], "batch_per_gpu": w["M"],
+                "gpu_launches": w["launches"], "params": w["param_count"], "e2e": w["e2e"], "losses_last_step": w["losses"]}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": (f"farmer_lstm MSE/Adam learner step (the reference's train_step), batch {M} x T={T} per GPU"
                                        if farmer else f"vtrace_mlp_actor_critic learner step, batch {M} x T={T} per GPU "
                                                       f"(BASELINE.json configs[3]; records of 1024 B)"),
-                          "batch_per_gpu": M, "global_batch": M * world, "ring_capacity_slots": ring_cap, "seq_len": T, "params": L.param_count,
-                          "optimizer": "adam lr 5e-4", "gemm_mode": args.gemm_mode,
+                          "batch_per_gpu": M, "global_batch": M * world, "ring_capacity_slots": main["ring_cap"], "seq_len": T,
+                          "params": main["param_count"], "optimizer": "adam lr 5e-4", "gemm_mode": args.gemm_mode,
                           "parallelism": f"dp{world} (batch sharded, NCCL sum-allreduce of the flat gradient arena)",
                           "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
                           "flops_per_step": None if farmer else 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
-               "gpu_launches": int(launches), "ms_per_step_instrumented": ms_per_step_prof,
-               "ms_per_step_by_rank": per_rank_ms[0], "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
-               "cpu_baseline": cpu, "losses_last_step": [float(x) for x in losses]}
+               "gpu_launches": int(launches), "ms_per_step_instrumented": main["ms_per_step_prof"],
+               "ms_per_step_by_rank": main["per_rank_ms"], "clocks": clocks, "e2e": main["e2e"], "roofline": roofline, "kernels": kernels,
+               "cpu_baseline": cpu, "losses_last_step": main["losses"],
+               "reference_workload": wl_block(ref_wl, f"farmer_lstm MSE/Adam learner step (cmd/libtorch_bench train_step), batch {M} x T={T} "
+                                                      f"per GPU: the configuration `bench.py --impl reference` times on the CPU"),
+               "strong_scaling": wl_block(strong_wl, f"vtrace_mlp_actor_critic learner step, GLOBAL batch {args.batch} x T={T} sharded over "
+                                                     f"{world} GPUs (SURVEY.md 8d config 4)")}
         print(json.dumps(out), flush=True)
-    L.close()
-    lib.fi_host_free(host_ptr)
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

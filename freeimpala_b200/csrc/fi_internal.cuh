@@ -34,6 +34,27 @@ size_t colsum_workspace_bytes(int m, int n);
 int launch_zero2(void* a, size_t a_bytes, void* b, size_t b_bytes, cudaStream_t stream);  // zero two small buffers, one kernel
 int launch_copy_words(float* dst, const float* src, int n, cudaStream_t stream);            // small device copy as a kernel
 
+// grad_reduce.cu: every split-K slab sum and bias column sum of a step in two launches (deterministic order).
+constexpr int kGradSegMax = 16;
+struct GradSeg {
+    const float* src;   // kind 0: [splits][stride] partial slabs; kind 1: [rows = splits][ld = stride] matrix
+    float* dst;         // n outputs in the gradient arena
+    float* scratch;     // kind 1: [rb][n] row-block partials
+    size_t stride;
+    int n, splits, kind, rb, rows_per_block;
+};
+struct GradSegTable {
+    GradSeg seg[kGradSegMax];
+    int first_block[kGradSegMax + 1];    // pass 2: first block of every segment
+    int first_block1[kGradSegMax + 1];   // pass 1: first block of every column-sum segment
+    int colsum_index[kGradSegMax];
+    int count = 0, num_colsum = 0;
+};
+int grad_table_add_slabs(GradSegTable* t, const float* slabs, int splits, size_t stride, int n, float* dst);
+int grad_table_add_colsum(GradSegTable* t, const float* x, int ld, int rows, int n, float* dst, float* scratch);
+size_t grad_colsum_scratch_bytes(int rows, int n);
+int launch_grad_finalize(GradSegTable* t, cudaStream_t st);
+
 // out[i] = sum_s partial[s * stride + i] in fixed order (deterministic split-K reduction).
 int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t n, float* out, cudaStream_t stream);
 
@@ -65,6 +86,8 @@ struct TcOut {
     float* colsum_out;                       // [4 * ceil(m/128), n] per-32-row column sums of the output (split-output path), or null
     HScale* out_hs = nullptr;                // fp16 format with a split output: receives the output's scale and max |x|
     const HScale* bias_hs = nullptr;         // fp16 format: a tensor whose amax bounds |bias| (the parameter arena)
+    int* deferred_splits = nullptr;          // non-null: leave the split-K slabs in the workspace ([splits][m*n], the output's
+                                             // layout) and report their number here (1: the product wrote `c` itself)
 };
 int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st);
 // fp16 format pre-passes: amax accumulates max |x| into hs->amax; split derives the scale from hs->amax (which must

@@ -123,8 +123,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        // a pipeline bug must surface as a launch error, never as a hung GPU
-        if (!done && ++spins > (1u << 26)) __trap();
+        // a pipeline bug must surface as a launch error, never as a hung GPU (a failed try_wait returns after the hardware's
+        // time limit, ~10 us: 2^20 of them are ~10 s, far beyond any legitimate wait)
+        if (!done && ++spins > (1u << 20)) __trap();
     } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -142,6 +143,17 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// one full 32-byte sector per lane, no L1 allocation (every byte is written once)
+__device__ __forceinline__ void st_global_v8u(void* p, const uint32_t* v) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -161,8 +173,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of another CTA of the cluster. Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier
+// does: what the arrival publishes here is the completion of tcgen05.ld's, ordered by tcgen05.fence::before_thread_sync.
+// (Round 1 used .release.cluster: a cluster-scope release is a full memory barrier -- 2000-3500 clocks per chunk on every
+// promotion warp while the TMA keeps the memory system busy, which is what made the CTA-pair mode lose; profiles/r2_gemm_trace.md.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier
 // (peer bit of the barrier address cleared, as cute::SM100_TMA_2SM_LOAD_2D does)
@@ -239,6 +255,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout).
@@ -290,34 +321,44 @@ __device__ __forceinline__ float warp_colsum32(const float* x, int lane) {
 // PAIR: two CTAs of a cluster (one SM pair) work on one 256 x BN tile with cta_group::2 MMAs. Each CTA holds its own
 // 128 rows of A and HALF of the B tile (BN/2 rows), the tensor core reads the other half from the peer: the B operand
 // traffic through each SM's shared memory halves (the 1-CTA kernel is shared-memory-bandwidth bound).
-template <int BN, bool PAIR = false>
+template <int BN, bool PAIR = false, bool W16 = false>
 struct TcCfg {
     static constexpr int kBRows = PAIR ? BN / 2 : BN;                 // rows of the B tile held by one CTA
     static constexpr int kStageBytes = 2 * (kTcBM + kBRows) * kTcRowBytes;  // A_hi, A_lo, B_hi, B_lo
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static_assert(!PAIR || BN == 128, "pair mode is built for BN = 128");
+    static_assert(!W16 || (BN == 128 && !PAIR), "16 promotion warps: 128-wide single-CTA tiles");
     static constexpr int kStages = PAIR ? 4 : (BN >= 128 ? 3 : 4);
     static constexpr int kTmemCols = 4 * BN;                          // 2 chunk buffers x [main | corr] (a power of two >= 32)
     // promotion + epilogue warps: two per TMEM lane quarter (each owns half of the tile's columns) once the tile is
     // wide enough, so that every SM sub-partition has two warps to interleave (one warp per scheduler issued at
     // ~0.25 instructions per clock and made the promotion side, not the MMAs, the critical path).
-    static constexpr int kPromoWarps = BN >= 64 ? 8 : 4;
-    static constexpr int kColsPerWarp = BN / (kPromoWarps / 4);
-    static constexpr int kThreads = kTcCtrlThreads + 32 * kPromoWarps;
-    static constexpr int kOutTileBytes = kPromoWarps * 32 * 128;      // per promotion warp: one 32 x 128 B staging tile
+    // W16 (products whose every tile ends in the fp16 split epilogue: forward, dgrad): TWO GROUPS of eight such warps that
+    // take the CTA's tiles alternately. A tile costs its promotion warps ~1700 clocks of promotions and ~5000 of epilogue
+    // (issue-bound: ~10 instructions per output element) against ~6800 clocks of MMAs, and the two TMEM chunk buffers let
+    // the issuer run only half a tile ahead: with one group the tensor pipe stood idle ~3000 clocks at every tile
+    // boundary (profiles/r2_gemm_trace.md). With two groups the epilogue of tile t overlaps ALL of tile t+1's MMAs,
+    // whose chunks the other group promotes. 2 control warps + 16: 576 threads, 112 registers each.
+    static constexpr int kCtrlWarps = W16 ? 2 : 4;                    // TMA producer, MMA issuer (W16: also the TMEM allocator), [allocator, idle]
+    static constexpr int kPromoWarps = W16 ? 16 : (BN >= 64 ? 8 : 4);
+    static constexpr int kGroupWarps = W16 ? 8 : kPromoWarps;         // promotion warps working on one tile
+    static constexpr int kColsPerWarp = BN / (kGroupWarps / 4);
+    static constexpr int kThreads = 32 * (kCtrlWarps + kPromoWarps);
+    static constexpr int kOutTileBytes = W16 ? 0 : kPromoWarps * 32 * 128;   // per promotion warp: one 32 x 128 B staging tile (W16: none)
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= kTcSmemLimit, "shared memory budget");
 };
 
 // One kernel for the three operand-major combinations. A_MN / B_MN: operand is MN-major (reduction index slow).
 // H: 3xFP16 operand format (fp16 hi / lo' pairs with per-tensor scales) instead of 3xTF32.
-template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H>
-__global__ void __launch_bounds__(TcCfg<BN, PAIR>::kThreads, 1)
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H, bool W16 = false>
+__global__ void __launch_bounds__(TcCfg<BN, PAIR, W16>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
                const TcShape sh, const TcEpilogue ep) {
-    using Cfg = TcCfg<BN, PAIR>;
+    using Cfg = TcCfg<BN, PAIR, W16>;
+    static_assert(!W16 || H, "16 promotion warps exist for the fp16 format only");
     constexpr int kStages = Cfg::kStages;
     static_assert(!H || BN >= 64, "the fp16 format needs 64-wide MN blocks");
     constexpr int BK = H ? kTcBKh : kTcBK;            // reduction elements per k-block
@@ -335,11 +376,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // barriers: full[kStages], empty[kStages], main_full[2], main_empty[2]
     const uint32_t out_tiles = smem_base + kStages * Cfg::kStageBytes;    // 1024-byte aligned: TMA-store staging, 8 KB per warp
     const uint32_t bar_base = out_tiles + Cfg::kOutTileBytes;
-    const uint32_t tmem_slot = bar_base + (2 * kStages + 6) * 8;
+    const uint32_t tmem_slot = bar_base + (2 * kStages + 8) * 8;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto main_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto main_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    // chunk barriers, one pair per (promotion group g, TMEM buffer b): with two tile-alternating groups (W16) each group
+    // sees every phase of ITS barriers in order (a barrier shared by the groups would advance by whole tiles while one of
+    // them is in its epilogue, and a parity wait cannot tell phases two apart)
+    auto main_full_bar_g = [&](int g, int b) { return bar_base + 8u * (2 * kStages + 2 * g + b); };
+    auto main_empty_bar_g = [&](int g, int b) { return bar_base + 8u * (2 * kStages + 4 + 2 * g + b); };
+    auto main_full_bar = [&](int b) { return main_full_bar_g(0, b); };
+    auto main_empty_bar = [&](int b) { return main_empty_bar_g(0, b); };
 
     const int warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index: provably warp-uniform
     float tmax_kernel = 0.f;  // fp16 format: running max |output| of this thread (published once at the end)
@@ -351,14 +397,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(main_full_bar(s), 1);
+        for (int s = 0; s < (W16 ? 4 : 2); s++) {   // s = 2 * group + buffer
+            mbar_init(main_full_bar_g(s >> 1, s & 1), 1);
             // one arrival per promotion warp; in pair mode the leader's barrier also collects the peer's warps
-            mbar_init(main_empty_bar(s), (PAIR ? 2 : 1) * Cfg::kPromoWarps);
+            mbar_init(main_empty_bar_g(s >> 1, s & 1), (PAIR ? 2 : 1) * Cfg::kGroupWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    constexpr int kAllocWarp = W16 ? 1 : 2;
+    if (warp == kAllocWarp) {
+        __syncwarp();
         if constexpr (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::kTmemCols)
                          : "memory");
@@ -471,11 +519,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             uint32_t phase = 0, mphase = 0;
             TraceLog tl;
             if (lane == 0) tl.init(sh.trace, 1);
+            // W16: the group that drains this tile's chunks, the group whose chunk each TMEM buffer holds (bit b; valid from
+            // the buffer's second use on) and the parity of the next drain expected from (group g, buffer b) (bit 2g + b)
+            uint32_t grp = 0, owner_bits = 0, drain_parity = 0, chunk_no = 0;
             for (int w = unit; w < total_work; w += num_units) {
                 const int split = w / tiles;
                 const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kc = kb0; kc < kb1; kc += kChunk) {
-                    mbar_wait(main_empty_bar(mb), mphase ^ 1);
+                    if constexpr (W16) {
+                        if (chunk_no >= 2) {   // the previous chunk in this TMEM buffer must have been promoted, by whichever group
+                            const uint32_t pg = (owner_bits >> mb) & 1u, bit = 2u * pg + (uint32_t)mb;
+                            mbar_wait(main_empty_bar_g((int)pg, mb), (drain_parity >> bit) & 1u);
+                            drain_parity ^= 1u << bit;
+                        }
+                        owner_bits = (owner_bits & ~(1u << mb)) | (grp << mb);
+                        chunk_no++;
+                    } else {
+                        mbar_wait(main_empty_bar(mb), mphase ^ 1);
+                    }
                     tl.ev(10);
                     tc_fence_after();
                     const uint32_t tmem_main = tmem_base_u + (uint32_t)(mb * 2 * BN), tmem_corr = tmem_main + BN;
@@ -522,20 +583,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     if (elect_one()) {
                         if constexpr (PAIR) tc_commit_pair(main_full_bar(mb));  // chunk complete, published to both CTAs
-                        else tc_commit(main_full_bar(mb));
+                        else tc_commit(main_full_bar_g((int)grp, mb));
                     }
                     __syncwarp();
                     tl.ev(14);
                     if (++mb == 2) { mb = 0; mphase ^= 1; }
                 }
+                if constexpr (W16) grp ^= 1u;   // tiles alternate between the two promotion groups
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= Cfg::kCtrlWarps) {
         // ===================== promotion + epilogue =====================
         constexpr int CW = Cfg::kColsPerWarp;     // columns of the tile owned by this warp
-        const int pw = warp - 4;
-        const int q = pw & 3;                     // TMEM lane quarter this warp may access (warp id % 4)
-        const int nc0 = (pw >> 2) * CW;           // first tile column of this warp
+        const int pw = warp - Cfg::kCtrlWarps;
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
+        const int ord = pw >> 2;                  // ordinal among the promotion warps of this quarter
+        const int group = W16 ? (ord >> 1) : 0;   // W16: which of the two tile-alternating groups
+        constexpr int kGroups = W16 ? 2 : 1;
+        const int nc0 = (W16 ? (ord & 1) : ord) * CW;   // first tile column of this warp
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int mb = 0;
         uint32_t mphase = 0;
@@ -546,14 +611,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         float out_mul = 1.f, out_scale = 1.f, acc_unit = 1.f;
         // TMA-split epilogues take the bias through the accumulator's initial value (loaded while the first chunk is
         // still being computed) instead of 64 dependent loads per thread on the epilogue's critical path
-        const bool bias_in_acc = ep.bias != nullptr && ep.tma_split;
+        constexpr bool kFastSplit = H && CW == 64;   // the fp16 split epilogue below
+        const bool bias_prefetch = ep.bias != nullptr && ep.tma_split;
+        const bool bias_in_acc = bias_prefetch && !kFastSplit;   // the fp16 split epilogue adds the prefetched bias itself
         if constexpr (H) {
             out_mul = ep.a_hs->inv * ep.b_hs->inv;
             acc_unit = ep.a_hs->scale * ep.b_hs->scale;
             if (ep.out_hs) {
                 const float bound = (float)sh.k * ep.a_hs->amax * ep.b_hs->amax + (ep.bias_hs ? ep.bias_hs->amax : 0.f);
                 out_scale = hscale_from_bound(bound);
-                if (blockIdx.x == 0 && threadIdx.x == kTcCtrlThreads) {
+                if (blockIdx.x == 0 && pw == 0 && lane == 0) {
                     ep.out_hs->scale = out_scale;
                     ep.out_hs->inv = 1.f / out_scale;
                     ep.out_hs->bound = bound;
@@ -562,28 +629,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         TraceLog tl;
         if (pw == 0 && lane == 0) tl.init(sh.trace, 2);
-        float bias_next[CW / 32];
+        float bias_next[CW / 32], bias_cur[CW / 32];
 #pragma unroll
-        for (int c = 0; c < CW / 32; c++) bias_next[c] = 0.f;
-        if (bias_in_acc && unit < total_work) {
-            const int fn0 = ((unit % tiles) % sh.num_n_blocks) * BN + nc0;
+        for (int c = 0; c < CW / 32; c++) bias_next[c] = bias_cur[c] = 0.f;
+        const int first_work = unit + group * num_units, work_step = kGroups * num_units;
+        // W16: the issuer numbers the chunks of all the CTA's tiles consecutively (buffer = number & 1); this group's
+        // tiles are every other one. No split-K on this path: every tile has the same number of chunks.
+        const int chunks_per_tile = (sh.kb_per_split + kChunk - 1) / kChunk;
+        int tile_seq = group;
+        uint32_t full_parity = 0;   // W16: parity of the next phase of main_full(group, b) this warp waits for (bit b)
+        if (bias_prefetch && first_work < total_work) {
+            const int fn0 = ((first_work % tiles) % sh.num_n_blocks) * BN + nc0;
 #pragma unroll
             for (int c = 0; c < CW / 32; c++) bias_next[c] = (fn0 + c * 32 + lane < sh.n) ? __ldg(ep.bias + fn0 + c * 32 + lane) : 0.f;
         }
-        for (int w = unit; w < total_work; w += num_units) {
+        for (int w = first_work; w < total_work; w += work_step, tile_seq += kGroups) {
             const int tile = w % tiles, split = w / tiles;
             const int m0 = (tile / sh.num_n_blocks) * kTileM + (int)cta_rank * kTcBM, n0 = (tile % sh.num_n_blocks) * BN;
             const int kb0 = split * sh.kb_per_split, kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < sh.m;
+            if constexpr (W16) mb = (tile_seq * chunks_per_tile) & 1;   // TMEM buffers alternate over ALL the CTA's chunks
             float acc[CW];
+            if (bias_prefetch && !bias_in_acc) {
+                // lane l holds the bias of column 32 c + l of this warp's range, fetched one tile ahead: the epilogue reads it
+                // with shuffles (no global-load latency on the epilogue's critical path: with 227 KB of shared memory there
+                // is no L1 left, every load is an L2 round trip)
+#pragma unroll
+                for (int c = 0; c < CW / 32; c++) bias_cur[c] = bias_next[c];
+                const int wn = w + work_step;
+                if (wn < total_work) {
+                    const int nn0 = ((wn % tiles) % sh.num_n_blocks) * BN + nc0;
+#pragma unroll
+                    for (int c = 0; c < CW / 32; c++) bias_next[c] = (nn0 + c * 32 + lane < sh.n) ? __ldg(ep.bias + nn0 + c * 32 + lane) : 0.f;
+                }
+            }
             if (bias_in_acc) {
                 // lane l holds the bias of columns l and 32 + l of this warp's range, fetched one tile ahead (below), and
                 // the initial accumulators are built with shuffles: no load latency at the start of a tile, where the
                 // MMAs of the next chunk are already waiting for the promotion warps
 #pragma unroll
                 for (int i = 0; i < CW; i++) acc[i] = __shfl_sync(0xFFFFFFFFu, i < 32 ? bias_next[0] : bias_next[CW > 32 ? 1 : 0], i & 31) * acc_unit;
-                const int wn = w + num_units;
+                const int wn = w + work_step;
                 if (wn < total_work) {
                     const int nn0 = ((wn % tiles) % sh.num_n_blocks) * BN + nc0;
 #pragma unroll
@@ -604,32 +691,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (n0 + nc0 + c * 32 < sh.n) mw[c] = __ldg(ep.mask_bits + (size_t)row * ep.mask_ldw + ((n0 + nc0) >> 5) + c);
             }
             for (int kc = kb0; kc < kb1; kc += kChunk) {
-                mbar_wait(main_full_bar(mb), mphase);
+                if constexpr (W16) {
+                    mbar_wait(main_full_bar_g(group, mb), (full_parity >> mb) & 1u);   // this group's own phase sequence per buffer
+                    full_parity ^= 1u << mb;
+                } else {
+                    mbar_wait(main_full_bar(mb), mphase);
+                }
                 tl.ev(20);
                 tc_fence_after();
-                if (!(sh.dbg & 4))
+                if (!(sh.dbg & 4)) {
+                    if constexpr (W16) {   // 18 warps: 96 registers per thread, 64 of them accumulators: the chunk comes in pieces
 #pragma unroll
-                for (int c = 0; c < CW / 32; c++) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + nc0 + c * 32), v);       // main
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + nc0 + c * 32), u);  // corr
-                    tmem_ld_wait();
+                        for (int c = 0; c < CW / 16; c++) {
+                            uint32_t v[8], u[8], v2[8], u2[8];
+                            tmem_ld8(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + nc0 + c * 16), v);           // main
+                            tmem_ld8(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + nc0 + c * 16), u);      // corr
+                            tmem_ld8(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + nc0 + c * 16 + 8), v2);
+                            tmem_ld8(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + nc0 + c * 16 + 8), u2);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i++)  // round-to-nearest promotion
-                        acc[c * 32 + i] += H ? fmaf(__uint_as_float(u[i]), kCorrMul, __uint_as_float(v[i]))
-                                             : __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                            for (int i = 0; i < 8; i++) {
+                                acc[c * 16 + i] += fmaf(__uint_as_float(u[i]), kCorrMul, __uint_as_float(v[i]));
+                                acc[c * 16 + 8 + i] += fmaf(__uint_as_float(u2[i]), kCorrMul, __uint_as_float(v2[i]));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CW / 32; c++) {
+                            uint32_t v[32], u[32];
+                            tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + nc0 + c * 32), v);       // main
+                            tmem_ld32(tmem_base + lane_base + (uint32_t)(mb * 2 * BN + BN + nc0 + c * 32), u);  // corr
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i++)  // round-to-nearest promotion
+                                acc[c * 32 + i] += H ? fmaf(__uint_as_float(u[i]), kCorrMul, __uint_as_float(v[i]))
+                                                     : __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (PAIR) mbar_arrive_cluster(mb ? leader_main_empty1 : leader_main_empty0);  // the MMA issuer lives in CTA 0
-                    else mbar_arrive(main_empty_bar(mb));
+                    else mbar_arrive(main_empty_bar_g(group, mb));
                 }
                 tl.ev(21);
                 if (++mb == 2) { mb = 0; mphase ^= 1; }
             }
             tl.ev(22);   // tile's k loop done: the epilogue runs until the next tag 20
             if (sh.dbg & 8) continue;
+            if constexpr (kFastSplit) {
+                if (ep.tma_split) {
+                    // ---- fp16 pair output (forward: bias + ReLU + ReLU bits; dgrad: ReLU mask + column sums) ----
+                    // This warp owns 32 rows x CW columns = CW * 2 bytes of halves per matrix row and output array;
+                    // everything is computed in registers (lane = row).
+                    const int rbase = m0 + q * 32, colw0 = n0 + nc0;
+                    if (colw0 < sh.n) {  // warp-uniform
+                        const float mul = out_mul * out_scale, inv_scale = 1.f / out_scale;   // powers of two: exact
+#pragma unroll
+                        for (int c = 0; c < CW / 32; c++) {
+                            const int col0 = colw0 + c * 32;
+                            float* a = acc + c * 32;
+                            if (ep.bias) {
+                                const float bs = bias_cur[c] * out_scale;
+#pragma unroll
+                                for (int i = 0; i < 32; i++) a[i] = fmaf(a[i], mul, __shfl_sync(0xFFFFFFFFu, bs, i));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) a[i] *= mul;
+                            }
+                            if (ep.relu) {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) a[i] = fmaxf(a[i], 0.f);
+                            }
+                            if (ep.mask_bits) {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) a[i] = ((mw[c] >> i) & 1u) ? a[i] : 0.f;
+                            }
+                            if (col0 < sh.n) {
+                                if (ep.mask_bits_out) {
+                                    // bit i = (a[i] > 0): 0 - bits(a[i]) is negative exactly for positive floats (+0 -> 0, negative
+                                    // floats -> positive integers), and a funnel shift moves its sign bit into the word: 2 integer
+                                    // instructions per element
+                                    uint32_t bits = 0;
+#pragma unroll
+                                    for (int i = 31; i >= 0; i--) bits = __funnelshift_l((uint32_t)(0 - __float_as_int(a[i])), bits, 1);
+                                    if (row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
+                                }
+                                if (ep.colsum_out) {
+                                    const float y1 = warp_colsum32(a, lane) * inv_scale;
+                                    if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
+                                }
+                            }
+                        }
+                        tl.ev(23);
+                        // hi = fp16(t), lo' = fp16((t - hi) * 2048), 16 columns at a time (two full 32-byte sectors per lane and
+                        // array), written straight from the registers. No shared memory on this path: every st.shared / ld.shared
+                        // of a staged epilogue (round 1: TMA store; then a coalescing transpose) queued behind the tensor core's
+                        // operand reads and the TMA fills (profiles/r2_gemm_trace.md).
+                        __half2 hmax = __float2half2_rn(0.f);
+                        __half* hi_row = static_cast<__half*>(ep.c_hi) + (size_t)row * ep.ldc_split + colw0;
+                        __half* lo_row = static_cast<__half*>(ep.c_lo) + (size_t)row * ep.ldc_split + colw0;
+#pragma unroll
+                        for (int j = 0; j < CW / 16; j++) {
+                            uint32_t h[8], l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) {
+                                const float t0 = acc[16 * j + 2 * e], t1 = acc[16 * j + 2 * e + 1];
+                                const __half2 h2 = __floats2half2_rn(t0, t1);
+                                hmax = __hmax2(hmax, __habs2(h2));
+                                const float2 hf = __half22float2(h2);
+                                // t - hf is exact in fp32; x 2048 folded into one fma
+                                const __half2 l2 = __floats2half2_rn(fmaf(t0, 2048.f, -2048.f * hf.x), fmaf(t1, 2048.f, -2048.f * hf.y));
+                                h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                l[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                            if (row_ok && colw0 + j * 16 < sh.n && !(sh.dbg & 32)) {   // n is a multiple of 16 on this path
+                                st_global_v8u(hi_row + j * 16, h);
+                                st_global_v8u(lo_row + j * 16, l);
+                            }
+                        }
+                        // max |output| from the rounded hi parts (within 2^-11 of the exact value; consumers only use it in bounds)
+                        tmax_kernel = fmaxf(tmax_kernel, fmaxf(__low2float(hmax), __high2float(hmax)) * (1.001f * inv_scale));
+                        tl.ev(29);
+                    }
+                    continue;
+                }
+            }
+            if constexpr (W16) {
+                __trap();   // the 16-warp variant is only launched for products that end in the fp16 split epilogue
+            } else {
             if constexpr (H) {
 #pragma unroll
                 for (int i = 0; i < CW; i++) acc[i] *= out_mul;   // powers of two: exact
@@ -654,89 +845,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int c = 0; c < CW / 32; c++) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) acc[c * 32 + i] = ((mw[c] >> i) & 1u) ? acc[c * 32 + i] : 0.f;
-                }
-            }
-            if constexpr (H) {
-                if (ep.tma_split) {
-                    // fp16 pair output (BN = 128: this warp owns 64 columns = one 128-byte row of halves per matrix row)
-                    if constexpr (CW == 64) {
-                        const uint32_t stage_tile = out_tiles + (uint32_t)pw * 4096u;  // 32 x 128 B, reused for hi then lo'
-                        const int rbase = m0 + q * 32, colw0 = n0 + nc0;
-                        if (colw0 < sh.n) {  // warp-uniform
-#pragma unroll
-                            for (int c = 0; c < 2; c++) {
-                                const int col0 = colw0 + c * 32;
-                                uint32_t bits = 0;
-#pragma unroll
-                                for (int i = 0; i < 32; i++) {
-                                    float t = acc[c * 32 + i];   // bias arrived through the accumulator
-                                    if (ep.relu) t = fmaxf(t, 0.f);
-                                    bits |= (t > 0.f ? 1u : 0u) << i;
-                                    acc[c * 32 + i] = t;
-                                }
-                                if (col0 < sh.n) {
-                                    if (ep.mask_bits_out && row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
-                                    if (ep.colsum_out) {
-                                        const float y1 = warp_colsum32(acc + c * 32, lane);
-                                        if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
-                                    }
-                                }
-                            }
-                            tl.ev(23);
-                            // hi parts first: converted, staged and handed to the TMA; the lo' parts (the longer arithmetic) are
-                            // computed while that bulk store reads the staging tile, so the wait before reusing it is short
-                            uint32_t wh[32];
-                            __half2 hmax = __float2half2_rn(0.f);
-#pragma unroll
-                            for (int e = 0; e < 32; e++) {
-                                acc[2 * e] *= out_scale;
-                                acc[2 * e + 1] *= out_scale;
-                                const __half2 h = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
-                                hmax = __hmax2(hmax, __habs2(h));
-                                wh[e] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
-                            // max |output| from the rounded hi parts (within 2^-11 of the exact value; consumers only use it in bounds)
-                            tmax_kernel = fmaxf(tmax_kernel, fmaxf(__low2float(hmax), __high2float(hmax)) * (1.001f / out_scale));
-                            tl.ev(24);
-                            if (lane == 0) tma_store_wait_read();   // the previous tile's lo' store: long finished
-                            __syncwarp();
-                            tl.ev(25);
-#pragma unroll
-                            for (int j = 0; j < 8; j++)   // 16-byte chunk j = columns 8j .. 8j+7, 128B swizzle
-                                st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
-                                              make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0 && !(sh.dbg & 32)) {
-                                tma_store_2d(&map_c_hi, stage_tile, colw0, rbase);
-                                tma_store_commit();
-                            }
-                            tl.ev(26);
-#pragma unroll
-                            for (int e = 0; e < 32; e++) {
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&wh[e]));
-                                // s - hf is exact in fp32; x 2048 folded into one fma
-                                const __half2 lo2 = __floats2half2_rn(fmaf(acc[2 * e], 2048.f, -2048.f * hf.x), fmaf(acc[2 * e + 1], 2048.f, -2048.f * hf.y));
-                                wh[e] = *reinterpret_cast<const uint32_t*>(&lo2);
-                            }
-                            tl.ev(27);
-                            if (lane == 0) tma_store_wait_read();
-                            __syncwarp();
-                            tl.ev(28);
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                st_shared_v4u(stage_tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
-                                              make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]));
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0 && !(sh.dbg & 32)) {
-                                tma_store_2d(&map_c_lo, stage_tile, colw0, rbase);
-                                tma_store_commit();
-                            }
-                            tl.ev(29);
-                        }
-                    }
-                    continue;
                 }
             }
             if (!H && ep.tma_split) {
@@ -850,20 +958,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (ep.mask_bits_out && lane < rows_here)
                     ep.mask_bits_out[(size_t)(rbase + lane) * ep.mask_ldw + (col0 >> 5)] = myword;
             }
+            }   // !W16
         }
     }
 
     if constexpr (H) {
-        if (warp >= 4 && ep.out_hs) {  // max |output| over everything this warp produced: one atomic per warp
+        if (warp >= Cfg::kCtrlWarps && ep.out_hs) {  // max |output| over everything this warp produced: one atomic per warp
             const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(tmax_kernel));
             if (lane == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&ep.out_hs->amax), wm);
         }
     }
-    if (warp >= 4 && lane == 0) tma_store_wait_all();  // staged output tiles must outlive their bulk stores
+    if (warp >= Cfg::kCtrlWarps && lane == 0) tma_store_wait_all();  // staged output tiles must outlive their bulk stores
     tc_fence_before();
     if constexpr (PAIR) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's barriers
     else __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         if constexpr (PAIR)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
@@ -1124,11 +1233,11 @@ size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k) {
     return s > 1 ? (size_t)s * m * n * sizeof(float) : 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool H, bool W16 = false>
 static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEpilogue& ep, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN, PAIR>;
+    using Cfg = TcCfg<BN, PAIR, W16>;
     static std::atomic<uint64_t> attr_devices{0};
-    FI_TRY(ensure_dynamic_smem(attr_devices, (const void*)gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, Cfg::kSmemBytes));
+    FI_TRY(ensure_dynamic_smem(attr_devices, (const void*)gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16>, Cfg::kSmemBytes));
     // profiling label: forward-like (NT), dgrad-like (NN), wgrad-like (TN, split-K)
     // (the odd-shaped products of a learner step -- layer 1's short K, the 17-wide head -- are timed under their own names)
     const bool narrow = sh.n < 64, short_k = !A_MN && sh.k < 256;
@@ -1150,10 +1259,10 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
     } else {
-        gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
-                                                                                      maps[5], sh, ep);
+        gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                           maps[4], maps[5], sh, ep);
     }
     return ls.done();
 }
@@ -1226,6 +1335,9 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
         FI_TRY(make_map(&maps[4], ep.c_hi, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false, half));
         FI_TRY(make_map(&maps[5], ep.c_lo, (uint64_t)n, (uint64_t)m, (uint64_t)out.ld_split, 32, false, half));
         ep.tma_split = 1;
+        if (half && (n % 16 || out.ld_split % 16 || ((reinterpret_cast<uintptr_t>(ep.c_hi) | reinterpret_cast<uintptr_t>(ep.c_lo)) & 31)))
+            return set_error(FI_ERR_ARG, "tcgen05 GEMM (fp16 format): a split output needs n and its row stride to be multiples of 16 "
+                                         "and 32-byte aligned arrays (n=%d, ld=%d)", n, out.ld_split);
     } else {
         maps[4] = maps[0];
         maps[5] = maps[0];
@@ -1241,7 +1353,12 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
                 : trans == 1 ? launch_variant<BNV, false, true, PAIRV, HV>(maps, sh, ep, grid, st)           \
                              : launch_variant<BNV, true, true, PAIRV, HV>(maps, sh, ep, grid, st))
     if (half) {
+        // products whose every tile ends in the fp16 split epilogue (forward, dgrad) run with 16 promotion warps
+        static const bool w16_on = [] { const char* e = getenv("FI_TC_W16"); return !e || atoi(e) != 0; }();
         if (bn == 128 && pair) rc = FI_TC(128, true, true);
+        else if (bn == 128 && w16_on && ep.tma_split && trans != 2)
+            rc = trans == 0 ? launch_variant<128, false, false, false, true, true>(maps, sh, ep, grid, st)
+                            : launch_variant<128, false, true, false, true, true>(maps, sh, ep, grid, st);
         else if (bn == 128) rc = FI_TC(128, false, true);
         else rc = FI_TC(64, false, true);
     } else if (bn == 128 && pair) rc = FI_TC(128, true, false);
@@ -1250,7 +1367,8 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     else rc = FI_TC(32, false, false);
 #undef FI_TC
     FI_TRY(rc);
-    if (sh.num_splits > 1) {
+    if (out.deferred_splits) *out.deferred_splits = sh.num_splits;
+    if (sh.num_splits > 1 && !out.deferred_splits) {
         const size_t total_out = (size_t)m * n;
         FI_TRY(launch_reduce_splits(static_cast<const float*>(workspace), sh.num_splits, total_out, total_out, out.c, st));
     }

@@ -36,8 +36,12 @@ struct AcTc {  // tensor-core path state, owned by the Player (Player::ac_tc)
     void *dhead_hi = nullptr, *dhead_lo = nullptr;   // [rows, 32], columns 17..31 stay zero
     float* dhead = nullptr;                          // fp16 format: the loss head's plain fp32 output [rows, 17]
     uint32_t* relu_bits[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [rows, 16] words: act_l > 0, bit-packed
-    float* colsum_part = nullptr;                    // [4 * ceil(rows/128), 512]: per-warp column sums from the dgrad epilogue
-    void* ws = nullptr; size_t ws_bytes = 0;         // split-K partials
+    // Every wgrad product keeps its split-K slabs and every dgrad epilogue its per-32-row column sums until the end of the
+    // backward pass, where two launches (grad_reduce.cu) sum them all into the gradient arena.
+    float* colsum_part[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [4 * ceil(rows/128), 512] left by the dgrad that produced d_l
+    float* colsum_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // row-block partials of the 5 layer biases + the head bias
+    void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // split-K slabs of the 5 layer wgrads + the head wgrad
+    size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
 static bool use_tc(const fi_learner* l) { return l->cfg.gemm_mode != FI_GEMM_SIMT && gemm_tc_available(); }
@@ -82,14 +86,16 @@ int ac_alloc(fi_learner* l, Player* p) {
         FI_CUDA_OK(cudaMalloc((void**)&t->dhead_lo, rows * kDheadLd * t->esz));
         FI_CUDA_OK(cudaMemset(t->dhead_hi, 0, rows * kDheadLd * t->esz));
         FI_CUDA_OK(cudaMemset(t->dhead_lo, 0, rows * kDheadLd * t->esz));
-        FI_CUDA_OK(cudaMalloc((void**)&t->colsum_part, 4 * ((rows + 127) / 128) * kHid * sizeof(float)));
-        size_t ws = 0;
-        auto upd = [&](size_t b) { if (b > ws) ws = b; };
-        upd(gemm_tc_split_workspace_bytes(2, kHid, kZDim, (int)rows));
-        upd(gemm_tc_split_workspace_bytes(2, kHid, kHid, (int)rows));
-        upd(gemm_tc_split_workspace_bytes(2, kHid, kHead, (int)rows));
-        t->ws_bytes = ws;
-        if (ws) FI_CUDA_OK(cudaMalloc(&t->ws, ws));
+        const int part_rows = 4 * (int)((rows + 127) / 128);
+        for (int i = 0; i < 5; i++) {
+            FI_CUDA_OK(cudaMalloc((void**)&t->colsum_part[i], (size_t)part_rows * kHid * sizeof(float)));
+            FI_CUDA_OK(cudaMalloc((void**)&t->colsum_scratch[i], grad_colsum_scratch_bytes(part_rows, kHid)));
+            t->ws_bytes[i] = gemm_tc_split_workspace_bytes(2, kHid, i == 0 ? kZDim : kHid, (int)rows);
+        }
+        FI_CUDA_OK(cudaMalloc((void**)&t->colsum_scratch[5], grad_colsum_scratch_bytes((int)rows, kHead)));
+        t->ws_bytes[5] = gemm_tc_split_workspace_bytes(2, kHid, kHead, (int)rows);
+        for (int i = 0; i < 6; i++)
+            if (t->ws_bytes[i]) FI_CUDA_OK(cudaMalloc(&t->ws[i], t->ws_bytes[i]));
         return FI_OK;
     }
     p->act.assign(5, nullptr);
@@ -108,15 +114,19 @@ void ac_free(Player* p) {
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.clear();
     if (AcTc* t = static_cast<AcTc*>(p->ac_tc)) {
-        void* f[] = {t->colsum_part, t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
+        void* f[] = {t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->dhead_hi, t->dhead_lo, t->d_hi[0],
                      t->d_hi[1], t->d_lo[0], t->d_lo[1], t->hs, t->dhead};
         for (void* x : f) if (x) cudaFree(x);
+        for (int i = 0; i < 6; i++) {
+            if (i < 5 && t->colsum_part[i]) cudaFree(t->colsum_part[i]);
+            if (t->colsum_scratch[i]) cudaFree(t->colsum_scratch[i]);
+            if (t->ws[i]) cudaFree(t->ws[i]);
+        }
         for (int i = 0; i < 5; i++) {
             if (t->act_hi[i]) cudaFree(t->act_hi[i]);
             if (t->act_lo[i]) cudaFree(t->act_lo[i]);
             if (t->relu_bits[i]) cudaFree(t->relu_bits[i]);
         }
-        if (t->ws) cudaFree(t->ws);
         delete t;
         p->ac_tc = nullptr;
     }
@@ -246,14 +256,21 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     }
     const SplitMat dhead{tc->dhead_hi, tc->dhead_lo, kDheadLd, HS(kHsDhead)};
     // head: db = colsum(dhead); dWh^T [512,17] = act4^T dhead, stored transposed as dWh [17,512];
-    // d4 = (dhead Wh) * relu'(act4)
-    if (H) FI_TRY(launch_colsum(tc->dhead, kHead, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
+    // d4 = (dhead Wh) * relu'(act4). Bias column sums and split-K slab sums are deferred to launch_grad_finalize below.
+    GradSegTable segs;
+    int splits = 1;
+    const int part_rows = 4 * ((rows + 127) / 128);
+    if (H) FI_TRY(grad_table_add_colsum(&segs, tc->dhead, kHead, rows, kHead, g + T[11].offset, tc->colsum_scratch[5]));
     else FI_TRY(launch_colsum2((float*)tc->dhead_hi, (float*)tc->dhead_lo, kDheadLd, rows, kHead, g + T[11].offset, p->colsum_ws, p->colsum_ws_bytes, st));
-    FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, TcOut{g + T[10].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, nullptr}, nullptr,
-                                0, nullptr, 0, tc->ws, tc->ws_bytes, st));
+    {
+        TcOut o{g + T[10].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, nullptr};
+        o.deferred_splits = &splits;
+        FI_TRY(launch_gemm_tc_split(2, kHid, kHead, rows, ACT(4), dhead, o, nullptr, 0, nullptr, 0, tc->ws[5], tc->ws_bytes[5], st));
+        if (splits > 1) FI_TRY(grad_table_add_slabs(&segs, (const float*)tc->ws[5], splits, (size_t)kHid * kHead, kHid * kHead, g + T[10].offset));
+    }
     int cur = 0, dslot = kHsD0;
     FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHead, dhead, W(10, kHid),
-                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32, tc->colsum_part,
+                                TcOut{nullptr, 0, tc->d_hi[cur], tc->d_lo[cur], kHid, 0, tc->relu_bits[4], nullptr, kHid / 32, tc->colsum_part[4],
                                       HS(dslot), nullptr},
                                 nullptr, 0, nullptr, 0, nullptr, 0, st));
     for (int layer = 4; layer >= 0; layer--) {
@@ -261,20 +278,23 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
         const SplitMat x = layer == 0 ? obs : ACT(layer - 1);
         const int k = layer == 0 ? kZDim : kHid;
         // bias gradient: the dgrad epilogue that produced d left per-32-row column sums (6.5 MB instead of re-reading 420 MB)
-        FI_TRY(launch_colsum(tc->colsum_part, kHid, 4 * ((rows + 127) / 128), kHid, g + T[2 * layer + 1].offset, p->colsum_ws,
-                             p->colsum_ws_bytes, st));
-        FI_TRY(launch_gemm_tc_split(2, kHid, k, rows, d, x, TcOut{g + T[2 * layer].offset, k, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr}, nullptr, 0,
-                                    nullptr, 0, tc->ws, tc->ws_bytes, st));
+        FI_TRY(grad_table_add_colsum(&segs, tc->colsum_part[layer], kHid, part_rows, kHid, g + T[2 * layer + 1].offset, tc->colsum_scratch[layer]));
+        {
+            TcOut o{g + T[2 * layer].offset, k, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
+            o.deferred_splits = &splits;
+            FI_TRY(launch_gemm_tc_split(2, kHid, k, rows, d, x, o, nullptr, 0, nullptr, 0, tc->ws[layer], tc->ws_bytes[layer], st));
+            if (splits > 1) FI_TRY(grad_table_add_slabs(&segs, (const float*)tc->ws[layer], splits, (size_t)kHid * k, kHid * k, g + T[2 * layer].offset));
+        }
         if (layer > 0) {
             FI_TRY(launch_gemm_tc_split(1, rows, kHid, kHid, d, W(2 * layer, kHid),
                                         TcOut{nullptr, 0, tc->d_hi[cur ^ 1], tc->d_lo[cur ^ 1], kHid, 0, tc->relu_bits[layer - 1], nullptr,
-                                              kHid / 32, tc->colsum_part, HS(dslot + 1), nullptr},
+                                              kHid / 32, tc->colsum_part[layer - 1], HS(dslot + 1), nullptr},
                                         nullptr, 0, nullptr, 0, nullptr, 0, st));
             cur ^= 1;
             dslot++;
         }
     }
-    return FI_OK;
+    return launch_grad_finalize(&segs, st);
 }
 
 int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int /*global_m*/) {

@@ -64,6 +64,13 @@ public:
     uint64_t getVersion() const { return version_; }                         // :130-132
     std::vector<char> getData() const { return data_; }                      // :135-138
     std::shared_ptr<Model> createCopy() const { return std::make_shared<Model>(data_, version_); }  // :149-156
+    // :140-147: replace the blob and the version (the MPI actor's TAG_WEIGHTS_RES handler, agent.h:139-142); like the
+    // reference, a blob of another size is ignored
+    void update(const std::vector<char>& new_data, uint64_t new_version) {
+        if (new_data.size() != data_.size()) return;
+        data_ = new_data;
+        version_ = new_version;
+    }
     const float* params() const { return reinterpret_cast<const float*>(data_.data()); }
 
 private:

@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
 REF_NN_SO = os.path.join(HERE, "_ref", "libfi_ref_nn.so")
 REF_HOST_SO = os.path.join(HERE, "_ref", "libfi_ref_host.so")
+DROPIN_BIN = os.path.join(HERE, "_ref", "agent_dropin")
 
 ELEMENT_SIZE = 1024
 REC_WORDS = 256
@@ -33,6 +34,10 @@ def build(ref: bool = True) -> None:
     """Compile liboracle.so and, when /root/reference is present, oracle/_ref."""
     targets = ["oracle"] + (["ref"] if ref else [])
     subprocess.run(["make", "-C", HERE, "-s"] + targets, check=True)
+    # drop-in proof (the reference's unmodified agent.h against fi_host.hpp): needs the reference and the built product library
+    lib = os.path.join(os.path.dirname(HERE), "freeimpala_b200", "_build", "libfreeimpala_b200.so")
+    if ref and os.path.exists(lib):
+        subprocess.run(["make", "-C", HERE, "-s", "dropin"], check=True)
 
 
 def _p(a, t=C.c_void_p):

@@ -78,3 +78,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(root, f), errors="replace").read()
                 assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text, f
+
+
+def test_reference_agent_header_compiles_against_the_host_shim(fi):
+    """The reference's actor (include/freeimpala/agent.h), UNMODIFIED and compiled from where it lies, builds and links
+    against freeimpala_b200/host/fi_host.hpp through the alias headers of oracle/ref_shim/dropin/ (INTEGRATION.md).
+    Runs only where the reference tree is present; the resulting binary is exercised on the GPU by tests/test_gpu_host.py."""
+    if not os.path.isdir("/root/reference/include/freeimpala"):
+        pytest.skip("/root/reference is not present on this box")
+    fi.load_library()
+    from oracle import pyoracle as po
+    subprocess.run(["make", "-C", os.path.join(U.ROOT, "oracle"), "-s", "dropin"], check=True)
+    assert os.path.exists(po.DROPIN_BIN)
+    # the alias headers define nothing of their own for the actor-private types: they re-export the reference's
+    text = open(os.path.join(U.ROOT, "oracle", "ref_shim", "dropin", "freeimpala", "data_structures.h")).read()
+    assert "using fi_reference::Buffer;" in text and "using SharedBuffer = fi_host::SharedBuffer;" in text
+    # without a device the binary fails loudly (no CPU fallback)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([po.DROPIN_BIN], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in r.stderr

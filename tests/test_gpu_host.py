@@ -52,3 +52,19 @@ def test_harness_batched_actor_inference(fi):
                         "--infer-every", 1)
     assert rc == 0, err[-2000:]
     assert out["actor_inference_rows"] == 8 * 2 * 10
+
+
+def test_reference_agent_runs_unmodified_against_the_shim(fi):
+    """Drop-in proof: oracle/_ref/agent_dropin is the reference's UNMODIFIED include/freeimpala/agent.h (+ its
+    metrics_tracker.h and the Buffer / BufferEntry / MessageTag / ELEMENT_SIZE definitions of its data_structures.h)
+    compiled against freeimpala_b200/host/fi_host.hpp through the alias headers INTEGRATION.md describes
+    (oracle/ref_shim/dropin/, built by `make -C oracle dropin` where /root/reference exists). 2 players x 2 reference
+    Agents write rand() trajectories through SharedBuffer::write and pull weights through ModelManager while the learner's
+    worker threads step on the GPU; the reference's own MetricsTracker counts the updates through the two calls
+    fi_host::Learner::trainModel keeps (learner.h:34,48)."""
+    from oracle import pyoracle as po
+    if not os.path.exists(po.DROPIN_BIN):
+        pytest.skip("oracle/_ref/agent_dropin was not built (needs /root/reference at build time)")
+    r = subprocess.run([po.DROPIN_BIN, "2", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "learner model updates 8" in r.stdout      # 2 players x (2 agents x 8 iterations / batch 4) updates

@@ -17,6 +17,9 @@ from oracle import pyoracle as po
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+# Free-running parameters against the reference's own after N Adam steps, relative L2 over all sampled elements (no
+# trimming). profiles/r2_parity.md has the measured values per case and GEMM mode.
+PARAM_TOL_VS_REFERENCE = 1e-5
 
 
 def _ac_learner(fi, m, t, **kw):
@@ -102,6 +105,36 @@ def test_step_through_ring_equals_staged_step(fi, oracle):
     assert np.array_equal(A.get_params(0), B.get_params(0))
     A.close()
     B.close()
+
+
+def test_next_gather_waits_for_the_consumer_of_the_previous_batch(fi):
+    """readBatch with no stream (the gather runs on the ring's own stream), an asynchronous step on the learner's stream,
+    and the next readBatch straight away: the second gather must not overwrite the batch buffer under the running step
+    (write-after-read on dev_batch). The step is long (256 x 100 on the fp32 FFMA path), the gather short."""
+    m, t = 256, 100
+    params = U.ac_params(4)
+    a = po.pack_vtrace_slots(*U.vtrace_batch(41, m, t))
+    b = po.pack_vtrace_slots(*U.vtrace_batch(42, m, t))
+    L = fi.Learner(1, 2 * m, t, m, model="mlp_actor_critic", gemm_mode="simt")
+    R = fi.Learner(1, 2 * m, t, m, model="mlp_actor_critic", gemm_mode="simt")
+    for X in (L, R):
+        X.set_params(0, params)
+    ring = L.getSharedBuffers()[0]
+    for slots in (a, b):
+        assert ring.write_many(slots) == m
+    first = ring.readBatch(m)            # stream=None: the ring's own stream
+    L.forward_backward(0, first)         # asynchronous, on the learner's stream
+    second = ring.readBatch(m)           # no synchronisation in between
+    got_a = L.get_grads(0)
+    L.forward_backward(0, second)
+    got_b = L.get_grads(0)
+    R.forward_backward(0, R.stage_batch(0, a))
+    want_a = R.get_grads(0)
+    R.forward_backward(0, R.stage_batch(0, b))
+    want_b = R.get_grads(0)
+    assert np.array_equal(got_a, want_a) and np.array_equal(got_b, want_b)
+    L.close()
+    R.close()
 
 
 def test_model_store_versions_and_checkpoint(fi, oracle):
@@ -207,11 +240,14 @@ def _farmer_learner(fi, m, t, **kw):
 
 
 @pytest.mark.parametrize("gemm_mode", ["simt", "auto", "tcgen05_f16"])
-@pytest.mark.parametrize("ci", [3, 4, 5, 6])
+@pytest.mark.parametrize("ci", [3, 4, 5, 6, 7])
 def test_farmer_step_vs_reference_golden(fi, oracle, ci, gemm_mode):
     """The CUDA FarmerLstm step against the reference's own libtorch train_step
     (cmd/libtorch_bench/main.cpp:117-135; fixtures from tools/make_golden.py). Case 3 is the README
-    shape / BASELINE.json configs[0]: batch 64, seq 100, MSE, Adam lr 5e-4."""
+    shape / BASELINE.json configs[0]: batch 64, seq 100, MSE, Adam lr 5e-4; case 7 is the shape bench.py's
+    reference arm and `--workload farmer` run: batch 1024, seq 100."""
+    if ci == 7 and gemm_mode == "simt":
+        pytest.skip("1024 x 100 is checked on the two tensor-core paths the bench runs (auto, tcgen05_f16)")
     g = np.load(os.path.join(U.GOLDEN, "farmer_step.npz"))
     stride = int(g["stride"][0])
     b, t, steps, ps, ys, bs = (int(v) for v in g[f"c{ci}_meta"])
@@ -239,9 +275,16 @@ def test_farmer_step_vs_reference_golden(fi, oracle, ci, gemm_mode):
         assert U.rel_l2(grads, O.grads()) < TOL                                     # vs the float64 oracle
         L.apply_update(0)
         parity.step(grads)
-    parity.check(L.get_params(0), TOL)
-    # against the reference's own parameters after N steps (every 997th element is stored)
-    assert U.trimmed_rel_l2(L.get_params(0)[::stride], g[f"c{ci}_params"]) < TOL
+    e_forced, e_trim, e_free = parity.check(L.get_params(0), TOL)
+    # Against the reference's OWN parameters after N free-running steps (every 997th element is stored), all elements, no
+    # trimming -- north_star: "parameter relative error <= 1e-5 after N steps" -- next to the same metric for the float64
+    # oracle against the reference (tests/test_oracle_pinned.py holds that one to 1e-5 as well).
+    got, ref = L.get_params(0)[::stride], g[f"c{ci}_params"]
+    e_ref, e_ref_max, e_orc_ref = U.rel_l2(got, ref), U.rel_max(got, ref), U.rel_l2(F.params()[::stride], ref)
+    print(f"farmer c{ci} {b}x{t} {loss}/{opt} x{steps} [{gemm_mode}] params after {steps} steps, untrimmed: cuda~reference rel_l2 "
+          f"{e_ref:.2e} (max {e_ref_max:.2e}); oracle~reference {e_orc_ref:.2e}; cuda~oracle free-running {e_free:.2e}, "
+          f"teacher-forced {e_forced:.2e}")
+    assert e_ref < PARAM_TOL_VS_REFERENCE, (e_ref, e_orc_ref)
     L.close()
 
 

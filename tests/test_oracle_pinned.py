@@ -20,7 +20,7 @@ def _farmer_case(g, ci):
     return b, t, steps, ps, ys, bs, loss, opt, float(g[f"c{ci}_lr"][0])
 
 
-@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_farmer_step_matches_reference_golden(oracle, ci):
     g = np.load(os.path.join(U.GOLDEN, "farmer_step.npz"))
     stride = int(g["stride"][0])

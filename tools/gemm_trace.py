@@ -56,6 +56,29 @@ def main():
                 sel_ss = sel[len(sel) // 8:] if len(sel) > 16 else sel   # steady state: skip the first eighth
                 print(f"  -> {NAMES.get(tag, tag):40s} n={sel.size:5d} median {np.median(sel_ss):8.0f}  p90 {np.percentile(sel_ss, 90):8.0f}  "
                       f"sum {sel.sum():9d} ({100.0 * sel.sum() / total:5.1f} %)")
+    # matched latencies of CTA 0: k-block i's loads issued (producer tag 2) -> seen full by the issuer (tag 11); stage released
+    # by the issuer's commit (tag 13 of k-block i) -> seen free by the producer (tag 1 of k-block i + stages); chunk committed
+    # (tag 14) -> seen by the promotion warp (tag 20); buffer released (tag 21) -> seen by the issuer (tag 10 two chunks later)
+    def times(cta, role, tag):
+        ev = buf[cta, role]
+        ev = ev[ev != 0]
+        return (ev[(ev & 0xFF) == tag] >> 8).astype(np.int64)
+    def report(name, a, b):
+        n = min(len(a), len(b))
+        if n < 8:
+            return
+        d = (b[:n] - a[:n])[n // 8:]
+        print(f"  {name:60s} median {np.median(d):8.0f}  p10 {np.percentile(d, 10):8.0f}  p90 {np.percentile(d, 90):8.0f}")
+    print("\nmatched latencies (CTA 0):")
+    issue, full = times(0, 0, 2), times(0, 1, 11)
+    report("loads issued -> stage seen full by the issuer", issue, full)
+    stages = int(os.environ.get("FI_TRACE_STAGES", "3"))
+    commit, free = times(0, 1, 13), times(0, 0, 1)
+    report(f"commit(empty) issued -> stage seen free by the producer ({stages} stages)", commit, free[stages:] if len(free) > stages else free)
+    cfull, seen = times(0, 1, 14), times(0, 2, 20)
+    report("commit(main_full) issued -> chunk seen by promotion warp 0", cfull, seen)
+    rel, got = times(0, 2, 21), times(0, 1, 10)
+    report("TMEM buffer released by warp 0 -> seen free by the issuer (2 chunks later)", rel, got[2:] if len(got) > 2 else got)
     # issuer timeline of CTA 0, a window in the steady state
     ev = buf[0, 1]
     ev = ev[ev != 0]
