@@ -346,7 +346,7 @@ def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: b
     if with_e2e:
         ring = L.getSharedBuffers()[0]
         cores_per_rank = max(1, host_cores() // world)
-        nw_copy = args.writers if args.writers > 0 else max(2, min(8, cores_per_rank - 1))
+        nw_copy = args.writers if args.writers > 0 else max(2, min(14, cores_per_rank - 2))
         nw_zc = int(os.environ.get("FI_BENCH_ZC_THREADS", "2"))  # in-place producers only take the ring lock: two threads keep the ring full
         zc_burst = int(os.environ.get("FI_BENCH_ZC_BURST", "64"))
 

@@ -9,8 +9,9 @@
 // denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= (lr/(1-b1^t)) * m/denom, with the bias
 // corrections evaluated in double on the host exactly as libtorch does.
 #include <cmath>
+#include <cstring>
 
-#include "fi_common.cuh"
+#include "fi_internal.cuh"
 
 namespace fi {
 
@@ -93,9 +94,11 @@ fused_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     }
 }
 
-int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m,
-               float* v, float grad_scale, cudaStream_t stream, float* snapshot, const double* losses_src, double* losses_dst) {
-    if (n == 0) return FI_OK;
+// Everything a launch of the optimiser kernel needs, by value: shared by the direct launch and by the CUDA-graph path of
+// the learner step, which re-parameterises ONE captured kernel node per step (step count -> bias corrections, snapshot and
+// loss read-back slots) with cudaGraphExecKernelNodeSetParams.
+int opt_launch_desc(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v, float grad_scale,
+                    float* snapshot, const double* losses_src, double* losses_dst, OptLaunchDesc* d) {
     if (!p || !g) return set_error(FI_ERR_ARG, "optimiser: null p/g");
     const bool adam = opt_kind == FI_OPT_ADAM || opt_kind == FI_OPT_ADAMW;
     if (!adam && opt_kind != FI_OPT_SGD) return set_error(FI_ERR_ARG, "optimiser: unknown kind %d", opt_kind);
@@ -119,11 +122,29 @@ int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const 
     size_t blocks = (n4 + kOptThreads - 1) / kOptThreads;
     const size_t cap = (size_t)kNumSMs * 8;  // whole waves of 8 resident CTAs per SM
     if (blocks > cap) blocks = cap;
-    // algorithmic traffic: read p,g,m,v + write p,m,v = 28 B/param (SGD: 12 B/param)
+    static_assert(sizeof(OptScalars) <= sizeof(d->scalars) && sizeof(OptExtras) <= sizeof(d->extras), "OptLaunchDesc storage");
+    d->func = adam ? (const void*)fused_opt_kernel<true> : (const void*)fused_opt_kernel<false>;
+    d->grid = (unsigned)blocks;
+    d->block = kOptThreads;
+    d->p = p; d->g = g; d->m = m; d->v = v; d->n = n;
+    memcpy(d->scalars, &s, sizeof(s));
     const OptExtras x{snapshot, losses_src, losses_src ? losses_dst : nullptr};
-    LaunchScope ls("fused_opt_kernel", stream, ((adam ? 28.0 : 12.0) + (snapshot ? 4.0 : 0.0)) * (double)n, kWorkBytes);
-    if (adam) fused_opt_kernel<true><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s, x);
-    else fused_opt_kernel<false><<<(unsigned)blocks, kOptThreads, 0, stream>>>(p, g, m, v, n, s, x);
+    memcpy(d->extras, &x, sizeof(x));
+    d->args[0] = &d->p; d->args[1] = &d->g; d->args[2] = &d->m; d->args[3] = &d->v; d->args[4] = &d->n;
+    d->args[5] = d->scalars; d->args[6] = d->extras;
+    // algorithmic traffic: read p,g,m,v + write p,m,v = 28 B/param (SGD: 12 B/param)
+    d->work_bytes = ((adam ? 28.0 : 12.0) + (snapshot ? 4.0 : 0.0)) * (double)n;
+    return FI_OK;
+}
+
+int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m,
+               float* v, float grad_scale, cudaStream_t stream, float* snapshot, const double* losses_src, double* losses_dst) {
+    if (n == 0) return FI_OK;
+    OptLaunchDesc d;
+    FI_TRY(opt_launch_desc(opt_kind, lr, step, n, p, g, m, v, grad_scale, snapshot, losses_src, losses_dst, &d));
+    LaunchScope ls("fused_opt_kernel", stream, d.work_bytes, kWorkBytes);
+    const cudaError_t e = cudaLaunchKernel(d.func, dim3(d.grid), dim3(d.block), d.args, 0, stream);
+    if (e != cudaSuccess) return set_error(FI_ERR_CUDA, "launch of fused_opt_kernel failed: %s", cudaGetErrorString(e));
     return ls.done();
 }
 

@@ -12,6 +12,17 @@ int ring_note_consumed(const void* dev_ptr, cudaStream_t consumer);
 int launch_opt(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v,
                float grad_scale, cudaStream_t stream, float* snapshot = nullptr, const double* losses_src = nullptr,
                double* losses_dst = nullptr);
+struct OptLaunchDesc {   // a launch of the fused optimiser kernel, by value (adam.cu)
+    const void* func;
+    unsigned grid, block;
+    float* p; const float* g; float* m; float* v; size_t n;
+    alignas(8) unsigned char scalars[48];
+    alignas(8) unsigned char extras[32];
+    void* args[7];
+    double work_bytes;
+};
+int opt_launch_desc(int opt_kind, double lr, int64_t step, size_t n, float* p, const float* g, float* m, float* v, float grad_scale,
+                    float* snapshot, const double* losses_src, double* losses_dst, OptLaunchDesc* d);
 int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount, const float* reward,
                        const float* value, const float* bootstrap, float rho_bar, float c_bar, float pg_rho_bar,
                        float lambda_, float* vs, float* pg_adv, cudaStream_t stream);

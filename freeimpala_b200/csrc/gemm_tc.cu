@@ -327,7 +327,7 @@ struct TcCfg {
     static constexpr int kStageBytes = 2 * (kTcBM + kBRows) * kTcRowBytes;  // A_hi, A_lo, B_hi, B_lo
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     static_assert(!PAIR || BN == 128, "pair mode is built for BN = 128");
-    static_assert(!W16 || (BN == 128 && !PAIR), "16 promotion warps: 128-wide single-CTA tiles");
+    static_assert(!W16 || BN == 128, "16 promotion warps: 128-wide tiles");
     static constexpr int kStages = PAIR ? 4 : (BN >= 128 ? 3 : 4);
     static constexpr int kTmemCols = 4 * BN;                          // 2 chunk buffers x [main | corr] (a power of two >= 32)
     // promotion + epilogue warps: two per TMEM lane quarter (each owns half of the tile's columns) once the tile is
@@ -582,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                     if (elect_one()) {
-                        if constexpr (PAIR) tc_commit_pair(main_full_bar(mb));  // chunk complete, published to both CTAs
+                        if constexpr (PAIR) tc_commit_pair(main_full_bar_g((int)grp, mb));  // chunk complete, published to both CTAs
                         else tc_commit(main_full_bar_g((int)grp, mb));
                     }
                     __syncwarp();
@@ -604,8 +604,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int mb = 0;
         uint32_t mphase = 0;
-        const uint32_t leader_main_empty0 = PAIR ? map_to_cta(main_empty_bar(0), 0) : 0u;
-        const uint32_t leader_main_empty1 = PAIR ? map_to_cta(main_empty_bar(1), 0) : 0u;
+        // pair mode: the MMA issuer lives in CTA 0, which collects both CTAs' releases of (this group's) chunk buffers
+        const uint32_t leader_main_empty0 = PAIR ? map_to_cta(main_empty_bar_g(group, 0), 0) : 0u;
+        const uint32_t leader_main_empty1 = PAIR ? map_to_cta(main_empty_bar_g(group, 1), 0) : 0u;
         // fp16 format: corr carries lo' = 2048 lo; the accumulator is in units of scale_a * scale_b
         constexpr float kCorrMul = H ? (1.f / 2048.f) : 1.f;
         float out_mul = 1.f, out_scale = 1.f, acc_unit = 1.f;
@@ -778,7 +779,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     for (int i = 31; i >= 0; i--) bits = __funnelshift_l((uint32_t)(0 - __float_as_int(a[i])), bits, 1);
                                     if (row_ok) ep.mask_bits_out[(size_t)row * ep.mask_ldw + (col0 >> 5)] = bits;
                                 }
-                                if (ep.colsum_out) {
+                                if (ep.colsum_out && m0 < sh.m) {   // (a pair's second CTA may lie wholly beyond the matrix)
                                     const float y1 = warp_colsum32(a, lane) * inv_scale;
                                     if (col0 + lane < sh.n) ep.colsum_out[(size_t)((m0 / kTcBM) * 4 + q) * sh.n + col0 + lane] = y1;
                                 }
@@ -1192,10 +1193,12 @@ static unsigned long long* tc_trace_buffer(int trans, int /*m*/, int n, int k) {
 
 static int pick_bn(int n, bool half = false) { return n > 64 ? 128 : ((n > 32 || half) ? 64 : 32); }
 
-// CTA-pair mode (cta_group::2, 256 x 128 tiles). Measured at the bench shape (profiles/r1_gemm_tc.md): the split-K
-// wgrad products (long K loops per tile) gain 11 % from the halved B traffic, while the K = 512 forward / dgrad
-// products lose 8 % to the cross-CTA chunk hand-over (4 chunks per tile, three MMA issues per k-slice instead of the
-// 1-CTA kernel's merged two). Default: pairs for the TN products only. FI_TC_PAIR=0 never, =2 always (experiments).
+// CTA-pair mode (cta_group::2, 256 x 128 tiles: each CTA loads its 128 rows of A and HALF of the B tile, 48 KB per
+// k-block instead of 64). Every big product of the learner step is bound by the L2 -> shared-memory fill rate (the TMA
+// loads of 148 CTAs draw 10-12.5 TB/s; profiles/r2_gemm_trace.md), so a quarter less operand traffic is a quarter less
+// time once nothing else is in the way. Round 1 measured pairs slower and kept them off in the fp16 format: their
+// promotion warps released each chunk with a cluster-scope release (a full memory barrier, 2000-3500 clocks per chunk).
+// With a CTA-scope release, pairs win. FI_TC_PAIR=0 never, =1 (default) wherever the tile shape allows, =2 the same.
 static int pair_policy() {
     static const int policy = [] {
         const char* e = getenv("FI_TC_PAIR");
@@ -1203,12 +1206,10 @@ static int pair_policy() {
     }();
     return policy;
 }
-// In the 3xFP16 format the MMAs take half as long per shared-memory byte delivered and the pair's cross-CTA hand-over
-// costs more than the halved B traffic returns (bench shape, TN: 121 us without pairs, 145 us with): pairs only on request.
 static bool use_pair(int trans, int m, int n, bool half) {
     const int policy = pair_policy();
     if (policy == 0 || pick_bn(n, half) != 128 || m < 2 * kTcBM) return false;
-    return policy >= 2 || (trans == 2 && !half);
+    return half || trans == 2 || policy >= 2;   // 3xTF32: the split-K wgrad products only, as measured in round 1
 }
 
 static int tc_splits(int trans, int m, int n, int k, bool pair, bool half = false) {
@@ -1355,8 +1356,12 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     if (half) {
         // products whose every tile ends in the fp16 split epilogue (forward, dgrad) run with 16 promotion warps
         static const bool w16_on = [] { const char* e = getenv("FI_TC_W16"); return !e || atoi(e) != 0; }();
-        if (bn == 128 && pair) rc = FI_TC(128, true, true);
-        else if (bn == 128 && w16_on && ep.tma_split && trans != 2)
+        const bool w16 = bn == 128 && w16_on && ep.tma_split && trans != 2;
+        if (w16 && pair)
+            rc = trans == 0 ? launch_variant<128, false, false, true, true, true>(maps, sh, ep, grid, st)
+                            : launch_variant<128, false, true, true, true, true>(maps, sh, ep, grid, st);
+        else if (bn == 128 && pair) rc = FI_TC(128, true, true);
+        else if (w16)
             rc = trans == 0 ? launch_variant<128, false, false, false, true, true>(maps, sh, ep, grid, st)
                             : launch_variant<128, false, true, false, true, true>(maps, sh, ep, grid, st);
         else if (bn == 128) rc = FI_TC(128, false, true);

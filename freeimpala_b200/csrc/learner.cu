@@ -208,6 +208,9 @@ void free_player(fi_learner* l, Player* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->store.pub_stream) cudaStreamSynchronize(p->store.pub_stream);
     if (p->infer_stream) cudaStreamSynchronize(p->infer_stream);
+    if (p->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
+    if (p->graph) cudaGraphDestroy((cudaGraph_t)p->graph);
+    p->graph_exec = p->graph = nullptr;
     if (p->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)p->nccl_comm);
     if (l->cfg.model == FI_MODEL_FARMER_LSTM) fi::farmer_free(p);
     else fi::ac_free(p);
@@ -428,33 +431,208 @@ int fi_learner_stage_batch(fi_learner* l, int player, const void* host, size_t n
     return FI_OK;
 }
 
-int fi_learner_forward_backward(fi_learner* l, int player, const fi_batch* b) {
-    Player* p = get_player(l, player);
-    if (!p || !b) return set_error(FI_ERR_ARG, "fi_learner_forward_backward: null argument");
-    if (b->num_slots == 0 || b->num_slots > l->cfg.batch_size || b->slot_bytes != l->cfg.entry_size * FI_ELEMENT_SIZE ||
-        !b->dev_ptr)
-        return set_error(FI_ERR_ARG, "fi_learner_forward_backward: batch [%zu x %zu B] does not match the learner (M<=%zu, S=%zu)",
-                         b->num_slots, b->slot_bytes, l->cfg.batch_size, l->cfg.entry_size);
-    FI_CUDA_OK(cudaSetDevice(l->cfg.device));
-    std::lock_guard<std::mutex> step_lock(p->step_mu);
-    if (b->stream && (cudaStream_t)b->stream != p->stream) {  // gather ran on another stream
-        FI_CUDA_OK(cudaEventRecord(p->batch_ready, (cudaStream_t)b->stream));
-        FI_CUDA_OK(cudaStreamWaitEvent(p->stream, p->batch_ready, 0));
-    }
-    const int m = (int)b->num_slots, t = (int)l->cfg.entry_size;
+namespace {
+// sum-allreduce of the flat gradient arena (+ the four loss sums) over NVLink, on the player's stream
+int enqueue_allreduce(fi_learner* l, Player* p) {
+    if (l->dp_world <= 1) return FI_OK;
+    if (!p->nccl_comm) return set_error(FI_ERR_STATE, "data parallelism configured but the communicator is missing");
+    NcclApi& n = nccl();
+    // timed as "nccl_allreduce_grads" (bus bytes of a ring all-reduce: 2(N-1)/N x the arena); it also absorbs the wait
+    // for the slowest rank, so it reads as skew + transfer
+    fi::LaunchScope ls("nccl_allreduce_grads", p->stream,
+                       2.0 * (l->dp_world - 1) / l->dp_world * 4.0 * (double)l->param_count, fi::kWorkBytes);
+    FI_NCCL_OK(n.GroupStart());
+    FI_NCCL_OK(n.AllReduce(p->grads, p->grads, l->param_count, ncclFloat, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
+    FI_NCCL_OK(n.AllReduce(p->d_losses, p->d_losses, 4, ncclDouble, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
+    FI_NCCL_OK(n.GroupEnd());
+    ls.done_external();
+    return FI_OK;
+}
+
+struct UpdateTicket {   // the host-side bookkeeping of one optimiser step
+    uint64_t steps_done;
+    bool publish;
+    int sn, slot;
+};
+
+// counters advance; the learner stream waits until the snapshot the optimiser kernel is about to write is free
+int begin_update(fi_learner* l, Player* p, UpdateTicket* u) {
+    p->opt_step++;
+    u->steps_done = p->steps_done.load(std::memory_order_relaxed) + 1;
+    p->version++;  // generateRandomData(): version++ (data_structures.h:121-127), then updateModel
+    u->publish = u->steps_done % (uint64_t)l->cfg.publish_every == 0;
+    u->sn = -1;
+    if (u->publish) FI_TRY(publish_begin(p, &u->sn));
+    u->slot = (int)(u->steps_done % Player::kLossRing);
+    return FI_OK;
+}
+
+// one kernel: the update, the model store's device snapshot and the loss read-back (into mapped pinned memory)
+int opt_desc_for(fi_learner* l, Player* p, const UpdateTicket& u, fi::OptLaunchDesc* d) {
+    return fi::opt_launch_desc(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m, p->adam_v, 1.0f,
+                               u.publish ? p->store.dev_snap[u.sn] : nullptr, p->d_losses, p->h_losses_dev + 4 * u.slot, d);
+}
+
+int finish_update(fi_learner* l, Player* p, const UpdateTicket& u) {
+    (void)l;
+    FI_CUDA_OK(cudaEventRecord(p->loss_ev[u.slot], p->stream));
+    p->steps_done.store(u.steps_done, std::memory_order_release);   // readers (losses_at, steps_done) see the event recorded
+    if (u.publish) FI_TRY(publish_end(p, p->version, u.sn));
+    return FI_OK;
+}
+
+int check_batch(fi_learner* l, const fi_batch* b, const char* who) {
+    if (!b) return set_error(FI_ERR_ARG, "%s: null argument", who);
+    if (b->num_slots == 0 || b->num_slots > l->cfg.batch_size || b->slot_bytes != l->cfg.entry_size * FI_ELEMENT_SIZE || !b->dev_ptr)
+        return set_error(FI_ERR_ARG, "%s: batch [%zu x %zu B] does not match the learner (M<=%zu, S=%zu)", who, b->num_slots, b->slot_bytes,
+                         l->cfg.batch_size, l->cfg.entry_size);
     // mean losses divide by the GLOBAL batch: under data parallelism that is the sum of the ranks' configured batch sizes
     // (all-reduced once in fi_learner_dp_init; shards may differ by one trajectory), so every rank must step full batches
-    if (l->dp_world > 1 && (size_t)m != l->cfg.batch_size)
-        return set_error(FI_ERR_STATE, "fi_learner_forward_backward: a partial batch (%d of %zu trajectories) cannot be combined with "
-                                       "data parallelism (the global batch size is fixed at fi_learner_dp_init)", m, l->cfg.batch_size);
+    if (l->dp_world > 1 && b->num_slots != l->cfg.batch_size)
+        return set_error(FI_ERR_STATE, "%s: a partial batch (%zu of %zu trajectories) cannot be combined with data parallelism (the "
+                                       "global batch size is fixed at fi_learner_dp_init)", who, b->num_slots, l->cfg.batch_size);
+    return FI_OK;
+}
+
+// forward + loss + backward of the configured model on the player's stream (caller holds step_mu)
+int enqueue_forward_backward(fi_learner* l, Player* p, const fi_batch* b) {
+    const int m = (int)b->num_slots, t = (int)l->cfg.entry_size;
     const int global_m = l->dp_world > 1 ? (int)l->dp_global_batch : m;
     if (l->cfg.model == FI_MODEL_FARMER_LSTM) FI_TRY(fi::farmer_forward_backward(l, p, (const float*)b->dev_ptr, m, t, global_m));
     else FI_TRY(fi::ac_forward_backward(l, p, (const float*)b->dev_ptr, m, t, global_m));
     p->last_rows = (size_t)m * t;
     p->grads_valid = true;
+    return FI_OK;
+}
+
+int wait_for_batch(Player* p, const fi_batch* b) {
+    if (b->stream && (cudaStream_t)b->stream != p->stream) {  // gather ran on another stream
+        FI_CUDA_OK(cudaEventRecord(p->batch_ready, (cudaStream_t)b->stream));
+        FI_CUDA_OK(cudaStreamWaitEvent(p->stream, p->batch_ready, 0));
+    }
+    return FI_OK;
+}
+
+bool graphs_enabled() {
+    static const bool on = [] { const char* e = getenv("FI_GRAPH"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
+void drop_graph(Player* p) {
+    if (p->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
+    if (p->graph) cudaGraphDestroy((cudaGraph_t)p->graph);   // kept alive: the optimiser's node handle belongs to it
+    p->graph_exec = nullptr;
+    p->graph = nullptr;
+    p->graph_opt_node = nullptr;
+}
+
+// The whole step -- forward, fused loss head, backward, gradient finalisation, (NCCL all-reduce,) optimiser -- as ONE CUDA
+// graph launch. The launch sequence of a step is static for a given batch buffer and batch size (every workspace is allocated at
+// creation, tensor maps and shapes do not change), except for the optimiser kernel's scalars: the bias corrections of the step
+// count, the model-store snapshot and the loss read-back slot. That one kernel node is re-parameterised each step
+// (cudaGraphExecKernelNodeSetParams); everything else replays. The step is captured the first time a (buffer, batch size) pair
+// is seen after two ordinary steps (first launches set kernel attributes and fill the tensor-map cache), and again whenever
+// the pair changes. Not used while per-kernel profiling is on (fi_prof_enable), or with FI_GRAPH=0.
+// Why: 30 launches per step cost the host 0.2-0.5 ms of enqueue time -- more than the whole step at batch 64 x 100 (BASELINE.json
+// configs[1]: 0.48 ms, launch-gap bound), and with 8 data-parallel ranks sharing 16 cores the slowest rank's enqueue jitter
+// becomes everyone's step time at the all-reduce.
+int step_with_graph(fi_learner* l, Player* p, const fi_batch* b, bool* used) {
+    *used = false;
+    if (!graphs_enabled() || p->graph_failed || fi::prof().on.load(std::memory_order_relaxed)) return FI_OK;
+    if (p->steps_done.load(std::memory_order_relaxed) < 2) return FI_OK;
+    const bool fresh = !p->graph_exec || p->graph_batch_ptr != b->dev_ptr || p->graph_batch_m != b->num_slots;
+    FI_TRY(wait_for_batch(p, b));
+    UpdateTicket u;
+    FI_TRY(begin_update(l, p, &u));
+    fi::OptLaunchDesc d;
+    FI_TRY(opt_desc_for(l, p, u, &d));
+    if (fresh) {
+        drop_graph(p);
+        const uint64_t n0 = fi::launch_counter().load();
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = e == cudaSuccess ? FI_OK : FI_ERR_CUDA;
+        if (rc == FI_OK) rc = enqueue_forward_backward(l, p, b);
+        if (rc == FI_OK) rc = enqueue_allreduce(l, p);
+        if (rc == FI_OK) {
+            fi::LaunchScope ls("fused_opt_kernel", p->stream, d.work_bytes, fi::kWorkBytes);
+            e = cudaLaunchKernel(d.func, dim3(d.grid), dim3(d.block), d.args, 0, p->stream);
+            rc = e == cudaSuccess ? ls.done() : FI_ERR_CUDA;
+        }
+        const cudaError_t e_end = cudaStreamEndCapture(p->stream, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == FI_OK && e_end == cudaSuccess && graph) {
+            // find the optimiser's node: the one kernel node running fused_opt_kernel
+            size_t nn = 0;
+            cudaGraphGetNodes(graph, nullptr, &nn);
+            std::vector<cudaGraphNode_t> nodes(nn);
+            cudaGraphGetNodes(graph, nodes.data(), &nn);
+            cudaGraphNode_t opt_node = nullptr;
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp;
+                if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == d.func) opt_node = nd;
+            }
+            if (opt_node && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                p->graph_exec = exec;
+                p->graph = graph;
+                graph = nullptr;
+                p->graph_opt_node = opt_node;
+                p->graph_batch_ptr = b->dev_ptr;
+                p->graph_batch_m = b->num_slots;
+                p->graph_kernels = fi::launch_counter().load() - n0;
+                fi::launch_counter().fetch_sub(p->graph_kernels);   // counted when the graph is launched
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!p->graph_exec) {
+            // capture is not possible here (e.g. a collective that cannot be captured): run this and all later steps as
+            // ordinary launches. Nothing captured has run; the host-side counters of begin_update stand.
+            cudaGetLastError();
+            p->graph_failed = true;
+            fprintf(stderr, "[freeimpala_b200] step graph capture failed (player %d): continuing with stream launches\n", p->index);
+            FI_TRY(enqueue_forward_backward(l, p, b));
+            FI_TRY(enqueue_allreduce(l, p));
+            fi::LaunchScope ls("fused_opt_kernel", p->stream, d.work_bytes, fi::kWorkBytes);
+            if (cudaLaunchKernel(d.func, dim3(d.grid), dim3(d.block), d.args, 0, p->stream) != cudaSuccess)
+                return set_error(FI_ERR_CUDA, "launch of fused_opt_kernel failed");
+            FI_TRY(ls.done());
+            FI_TRY(fi::ring_note_consumed(b->dev_ptr, p->stream));
+            *used = true;
+            return finish_update(l, p, u);
+        }
+    } else {
+        cudaKernelNodeParams kp = {};
+        kp.func = const_cast<void*>(d.func);
+        kp.gridDim = dim3(d.grid);
+        kp.blockDim = dim3(d.block);
+        kp.sharedMemBytes = 0;
+        kp.kernelParams = d.args;
+        kp.extra = nullptr;
+        FI_CUDA_OK(cudaGraphExecKernelNodeSetParams((cudaGraphExec_t)p->graph_exec, (cudaGraphNode_t)p->graph_opt_node, &kp));
+        p->last_rows = b->num_slots * l->cfg.entry_size;
+        p->grads_valid = true;
+    }
+    FI_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec, p->stream));
+    fi::count_launch(p->graph_kernels);
     // the batch buffer may be rewritten by its ring's next gather once everything enqueued above has read it
     FI_TRY(fi::ring_note_consumed(b->dev_ptr, p->stream));
-    return FI_OK;
+    *used = true;
+    return finish_update(l, p, u);
+}
+}  // namespace
+
+int fi_learner_forward_backward(fi_learner* l, int player, const fi_batch* b) {
+    Player* p = get_player(l, player);
+    if (!p) return FI_ERR_ARG;
+    FI_TRY(check_batch(l, b, "fi_learner_forward_backward"));
+    FI_CUDA_OK(cudaSetDevice(l->cfg.device));
+    std::lock_guard<std::mutex> step_lock(p->step_mu);
+    FI_TRY(wait_for_batch(p, b));
+    FI_TRY(enqueue_forward_backward(l, p, b));
+    // the batch buffer may be rewritten by its ring's next gather once everything enqueued above has read it
+    return fi::ring_note_consumed(b->dev_ptr, p->stream);
 }
 
 int fi_learner_apply_update(fi_learner* l, int player) {
@@ -462,37 +640,26 @@ int fi_learner_apply_update(fi_learner* l, int player) {
     if (!p) return FI_ERR_ARG;
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
     std::lock_guard<std::mutex> step_lock(p->step_mu);
-    if (l->dp_world > 1) {  // sum-allreduce of the flat gradient arena over NVLink
-        if (!p->nccl_comm) return set_error(FI_ERR_STATE, "data parallelism configured but the communicator is missing");
-        NcclApi& n = nccl();
-        // timed as "nccl_allreduce_grads" (bus bytes of a ring all-reduce: 2(N-1)/N x the arena); it also absorbs the wait
-        // for the slowest rank, so it reads as skew + transfer
-        fi::LaunchScope ls("nccl_allreduce_grads", p->stream,
-                           2.0 * (l->dp_world - 1) / l->dp_world * 4.0 * (double)l->param_count, fi::kWorkBytes);
-        FI_NCCL_OK(n.GroupStart());
-        FI_NCCL_OK(n.AllReduce(p->grads, p->grads, l->param_count, ncclFloat, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
-        FI_NCCL_OK(n.AllReduce(p->d_losses, p->d_losses, 4, ncclDouble, ncclSum, (ncclComm_t)p->nccl_comm, p->stream));
-        FI_NCCL_OK(n.GroupEnd());
-        ls.done_external();
-    }
-    p->opt_step++;
-    const uint64_t steps_done = p->steps_done.load(std::memory_order_relaxed) + 1;
-    p->version++;  // generateRandomData(): version++ (data_structures.h:121-127), then updateModel
-    const bool publish = steps_done % (uint64_t)l->cfg.publish_every == 0;
-    int sn = -1;
-    if (publish) FI_TRY(publish_begin(p, &sn));
-    // one kernel: the update, the model store's device snapshot and the loss read-back (into mapped pinned memory)
-    const int slot = (int)(steps_done % Player::kLossRing);
+    FI_TRY(enqueue_allreduce(l, p));
+    UpdateTicket u;
+    FI_TRY(begin_update(l, p, &u));
     FI_TRY(fi::launch_opt(l->cfg.optimizer, l->cfg.lr, p->opt_step, l->param_count, p->params, p->grads, p->adam_m,
-                          p->adam_v, 1.0f, p->stream, publish ? p->store.dev_snap[sn] : nullptr, p->d_losses,
-                          p->h_losses_dev + 4 * slot));
-    FI_CUDA_OK(cudaEventRecord(p->loss_ev[slot], p->stream));
-    p->steps_done.store(steps_done, std::memory_order_release);   // readers (losses_at, steps_done) see the event recorded
-    if (publish) FI_TRY(publish_end(p, p->version, sn));
-    return FI_OK;
+                          p->adam_v, 1.0f, p->stream, u.publish ? p->store.dev_snap[u.sn] : nullptr, p->d_losses,
+                          p->h_losses_dev + 4 * u.slot));
+    return finish_update(l, p, u);
 }
 
 int fi_learner_step(fi_learner* l, int player, const fi_batch* batch) {
+    Player* p = get_player(l, player);
+    if (!p) return FI_ERR_ARG;
+    FI_TRY(check_batch(l, batch, "fi_learner_step"));
+    FI_CUDA_OK(cudaSetDevice(l->cfg.device));
+    {
+        std::lock_guard<std::mutex> step_lock(p->step_mu);
+        bool used = false;
+        FI_TRY(step_with_graph(l, p, batch, &used));
+        if (used) return FI_OK;
+    }
     FI_TRY(fi_learner_forward_backward(l, player, batch));
     return fi_learner_apply_update(l, player);
 }
@@ -585,17 +752,28 @@ void* fi_learner_param_ptr(fi_learner* l, int player) {
 }
 
 // ---- batched actor policy inference --------------------------------
-int fi_learner_infer(fi_learner* l, int player, const float* obs_or_z, const float* x, size_t rows, size_t t,
-                     float* logits, float* values) {
-    Player* p = get_player(l, player);
-    if (!p || !obs_or_z || rows == 0) return set_error(FI_ERR_ARG, "fi_learner_infer: null argument");
+// The hook is the comment in Agent::simulateGame (reference include/freeimpala/agent.h:52-56): every actor asks, for its
+// player, for the policy at its current observations. Concurrent callers are COMBINED: requests queue per player, the
+// first caller that finds no forward in flight becomes the leader, takes everything that is pending (up to
+// kInferMaxRows), packs the observations into one pinned buffer, and runs ONE host->device copy, ONE forward on the
+// newest published snapshot of the weights, ONE device->host copy and one stream synchronisation for the whole batch;
+// the other callers sleep on a condition variable and find their rows filled in. While a forward runs the next batch
+// accumulates, so 64 actors cost about two forwards per round instead of 64 (round 1: one synchronous forward per
+// caller under a mutex). Batches of kInferTcRows rows or more run the tensor-core forward of the learner step.
+namespace {
+constexpr size_t kInferMaxRows = 16384;
+
+int run_infer_batch(fi_learner* l, Player* p, const std::vector<fi::InferReq*>& batch, size_t rows, size_t t) {
     const bool farmer = l->cfg.model == FI_MODEL_FARMER_LSTM;
-    if (farmer && (!x || t == 0 || !values)) return set_error(FI_ERR_ARG, "fi_learner_infer: the farmer model needs z, x, t and values");
     FI_CUDA_OK(cudaSetDevice(l->cfg.device));
-    std::lock_guard<std::mutex> infer_lock(p->infer_mu);
-    const size_t in_elems = farmer ? rows * t * fi::kZDim : rows * fi::kZDim;
+    const size_t row_in = farmer ? t * fi::kZDim : fi::kZDim;
+    const size_t in_elems = rows * row_in;
     const size_t out_cols = farmer ? 1 : fi::kHead;
-    if (rows > p->inf_rows_cap || (farmer && t > p->inf_t_cap)) {  // grow the inference workspaces
+    if (rows > p->inf_rows_cap || (farmer && t > p->inf_t_cap)) {  // grow the inference workspaces (with head-room)
+        size_t cap = p->inf_rows_cap ? p->inf_rows_cap : 64;
+        while (cap < rows) cap *= 2;
+        const size_t tcap = farmer ? (t > p->inf_t_cap ? t : p->inf_t_cap) : 0;
+        const size_t cap_in = cap * (farmer ? tcap * fi::kZDim : fi::kZDim);
         FI_CUDA_OK(cudaStreamSynchronize(p->infer_stream));
         if (p->inf_in) cudaFree(p->inf_in);
         if (p->inf_x) cudaFree(p->inf_x);
@@ -605,30 +783,32 @@ int fi_learner_infer(fi_learner* l, int player, const float* obs_or_z, const flo
         if (p->inf_host_out) cudaFreeHost(p->inf_host_out);
         p->inf_in = p->inf_x = p->inf_out = p->inf_host_in = p->inf_host_x = p->inf_host_out = nullptr;
         p->inf_rows_cap = 0;
-        FI_CUDA_OK(cudaMalloc((void**)&p->inf_in, in_elems * sizeof(float)));
-        FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_in, in_elems * sizeof(float), cudaHostAllocPortable));
-        FI_CUDA_OK(cudaMalloc((void**)&p->inf_out, rows * out_cols * sizeof(float)));
-        FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_out, rows * out_cols * sizeof(float), cudaHostAllocPortable));
+        FI_CUDA_OK(cudaMalloc((void**)&p->inf_in, cap_in * sizeof(float)));
+        FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_in, cap_in * sizeof(float), cudaHostAllocPortable));
+        FI_CUDA_OK(cudaMalloc((void**)&p->inf_out, cap * out_cols * sizeof(float)));
+        FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_out, cap * out_cols * sizeof(float), cudaHostAllocPortable));
         if (farmer) {
-            FI_CUDA_OK(cudaMalloc((void**)&p->inf_x, rows * fi::kXDim * sizeof(float)));
-            FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_x, rows * fi::kXDim * sizeof(float), cudaHostAllocPortable));
-            FI_TRY(fi::farmer_infer_alloc(l, p, rows, t));
+            FI_CUDA_OK(cudaMalloc((void**)&p->inf_x, cap * fi::kXDim * sizeof(float)));
+            FI_CUDA_OK(cudaHostAlloc((void**)&p->inf_host_x, cap * fi::kXDim * sizeof(float), cudaHostAllocPortable));
+            FI_TRY(fi::farmer_infer_alloc(l, p, cap, tcap));
         } else {
-            FI_TRY(fi::ac_infer_alloc(l, p, rows));
+            FI_TRY(fi::ac_infer_alloc(l, p, cap));
         }
-        p->inf_rows_cap = rows;
-        p->inf_t_cap = t;
+        p->inf_rows_cap = cap;
+        p->inf_t_cap = tcap;
     }
     cudaStream_t st = p->infer_stream;
-    memcpy(p->inf_host_in, obs_or_z, in_elems * sizeof(float));
-    FI_CUDA_OK(cudaMemcpyAsync(p->inf_in, p->inf_host_in, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (farmer) {
-        memcpy(p->inf_host_x, x, rows * fi::kXDim * sizeof(float));
-        FI_CUDA_OK(cudaMemcpyAsync(p->inf_x, p->inf_host_x, rows * fi::kXDim * sizeof(float), cudaMemcpyHostToDevice, st));
+    size_t r0 = 0;
+    for (const fi::InferReq* q : batch) {   // pack the callers' rows back to back
+        memcpy(p->inf_host_in + r0 * row_in, q->obs, q->rows * row_in * sizeof(float));
+        if (farmer) memcpy(p->inf_host_x + r0 * fi::kXDim, q->x, q->rows * fi::kXDim * sizeof(float));
+        r0 += q->rows;
     }
+    FI_CUDA_OK(cudaMemcpyAsync(p->inf_in, p->inf_host_in, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (farmer) FI_CUDA_OK(cudaMemcpyAsync(p->inf_x, p->inf_host_x, rows * fi::kXDim * sizeof(float), cudaMemcpyHostToDevice, st));
     {
         ModelStore& s = p->store;
-        std::lock_guard<std::mutex> g(s.mu);  // pins the newest snapshot against the learner's next D2D
+        std::lock_guard<std::mutex> g(s.mu);  // pins the newest snapshot against the learner's next write into it
         const int sn = s.newest_snap;
         FI_CUDA_OK(cudaStreamWaitEvent(st, s.snap_ready[sn], 0));
         if (farmer) FI_TRY(fi::farmer_infer(l, p, s.dev_snap[sn], p->inf_in, p->inf_x, rows, t, p->inf_out, st));
@@ -637,16 +817,76 @@ int fi_learner_infer(fi_learner* l, int player, const float* obs_or_z, const flo
         s.infer_recorded[sn] = true;
     }
     FI_CUDA_OK(cudaMemcpyAsync(p->inf_host_out, p->inf_out, rows * out_cols * sizeof(float), cudaMemcpyDeviceToHost, st));
-    FI_CUDA_OK(cudaStreamSynchronize(st));
-    if (farmer) {
-        memcpy(values, p->inf_host_out, rows * sizeof(float));
-    } else {
-        for (size_t r = 0; r < rows; r++) {
-            const float* o = p->inf_host_out + r * fi::kHead;
-            if (logits) memcpy(logits + r * fi::kNumActions, o, fi::kNumActions * sizeof(float));
-            if (values) values[r] = o[fi::kNumActions];
+    FI_CUDA_OK(cudaStreamSynchronize(st));   // one synchronisation per BATCH: the callers need their rows on the host
+    r0 = 0;
+    for (const fi::InferReq* q : batch) {
+        if (farmer) {
+            memcpy(q->values, p->inf_host_out + r0, q->rows * sizeof(float));
+        } else {
+            for (size_t r = 0; r < q->rows; r++) {
+                const float* o = p->inf_host_out + (r0 + r) * fi::kHead;
+                if (q->logits) memcpy(q->logits + r * fi::kNumActions, o, fi::kNumActions * sizeof(float));
+                if (q->values) q->values[r] = o[fi::kNumActions];
+            }
         }
+        r0 += q->rows;
     }
+    return FI_OK;
+}
+}  // namespace
+
+int fi_learner_infer(fi_learner* l, int player, const float* obs_or_z, const float* x, size_t rows, size_t t,
+                     float* logits, float* values) {
+    Player* p = get_player(l, player);
+    if (!p || !obs_or_z || rows == 0) return set_error(FI_ERR_ARG, "fi_learner_infer: null argument");
+    const bool farmer = l->cfg.model == FI_MODEL_FARMER_LSTM;
+    if (farmer && (!x || t == 0 || !values)) return set_error(FI_ERR_ARG, "fi_learner_infer: the farmer model needs z, x, t and values");
+    if (rows > kInferMaxRows) return set_error(FI_ERR_ARG, "fi_learner_infer: at most %zu rows per call", kInferMaxRows);
+    fi::InferReq req{obs_or_z, x, rows, farmer ? t : 0, logits, values, FI_OK, false};
+    std::unique_lock<std::mutex> lk(p->infer_mu);
+    p->infer_pending.push_back(&req);
+    p->infer_calls++;
+    while (!req.done) {
+        if (p->infer_busy) {   // a forward is in flight: this request rides in the next batch
+            p->infer_cv.wait(lk);
+            continue;
+        }
+        // become the leader: everything pending that fits one forward (the farmer model batches equal sequence lengths)
+        p->infer_busy = true;
+        std::vector<fi::InferReq*> batch;
+        size_t total = 0;
+        const size_t bt = p->infer_pending.front()->t;
+        for (auto it = p->infer_pending.begin(); it != p->infer_pending.end();) {
+            if ((*it)->t == bt && total + (*it)->rows <= kInferMaxRows) {
+                total += (*it)->rows;
+                batch.push_back(*it);
+                it = p->infer_pending.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        const int rc = run_infer_batch(l, p, batch, total, bt);
+        lk.lock();
+        for (fi::InferReq* q : batch) {
+            q->status = rc;
+            q->done = true;
+        }
+        p->infer_batches++;
+        p->infer_rows += total;
+        p->infer_busy = false;
+        p->infer_cv.notify_all();
+    }
+    return req.status;
+}
+
+int fi_learner_infer_stats(fi_learner* l, int player, uint64_t* calls, uint64_t* batches, uint64_t* rows) {
+    Player* p = get_player(l, player);
+    if (!p) return FI_ERR_ARG;
+    std::lock_guard<std::mutex> lk(p->infer_mu);
+    if (calls) *calls = p->infer_calls;
+    if (batches) *batches = p->infer_batches;
+    if (rows) *rows = p->infer_rows;
     return FI_OK;
 }
 

@@ -56,6 +56,16 @@ struct PublishTicket {                      // argument of the publication host 
     uint64_t version;
 };
 
+struct InferReq {   // one caller of fi_learner_infer waiting for its rows
+    const float* obs;
+    const float* x;
+    size_t rows, t;
+    float* logits;
+    float* values;
+    int status;
+    bool done;
+};
+
 struct Player {
     int index = 0;
     std::mutex step_mu;         // serialises enqueueing on `stream` against checkpoint / arena access
@@ -86,14 +96,26 @@ struct Player {
     unsigned char* stage_dev = nullptr;  // staged batch (fi_learner_stage_batch)
     unsigned char* stage_host = nullptr; // pinned bounce buffer for pageable sources
     size_t stage_bytes = 0;
-    // inference
+    // inference: concurrent callers are combined into one forward per batch (fi_learner_infer)
     std::mutex infer_mu;
+    std::condition_variable infer_cv;
+    std::vector<InferReq*> infer_pending;
+    bool infer_busy = false;
+    uint64_t infer_calls = 0, infer_batches = 0, infer_rows = 0;
     cudaStream_t infer_stream = nullptr;
     float *inf_in = nullptr, *inf_x = nullptr, *inf_out = nullptr;
     float *inf_host_in = nullptr, *inf_host_x = nullptr, *inf_host_out = nullptr;  // pinned
     std::vector<float*> inf_act;
     void* inf_model_ws = nullptr;
     size_t inf_rows_cap = 0, inf_t_cap = 0;
+    // the step as one CUDA graph (learner.cu step_with_graph)
+    void* graph_exec = nullptr;       // cudaGraphExec_t
+    void* graph = nullptr;            // cudaGraph_t it was instantiated from
+    void* graph_opt_node = nullptr;   // cudaGraphNode_t of the optimiser kernel, re-parameterised every step
+    const void* graph_batch_ptr = nullptr;
+    size_t graph_batch_m = 0;
+    uint64_t graph_kernels = 0;       // launches inside the graph (fi_kernel_launch_count)
+    bool graph_failed = false;
     ModelStore store;
     uint64_t checkpoint_counter = 0;
     std::mutex save_mu;         // one fi_model_save per player at a time
@@ -119,6 +141,7 @@ int ac_alloc(fi_learner* l, Player* p);
 void ac_free(Player* p);
 int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int t, int global_m);
 int ac_infer_alloc(fi_learner* l, Player* p, size_t rows);
+void ac_infer_free(Player* p);
 int ac_infer(fi_learner* l, Player* p, const float* params, const float* obs_dev, size_t rows, float* out_dev,
              cudaStream_t stream);
 // ReLU outputs of hidden layer `layer` of the last forward: *a (+ *lo when stored as a hi/lo pair)

@@ -108,7 +108,10 @@ int ac_alloc(fi_learner* l, Player* p) {
     return FI_OK;
 }
 
+void ac_infer_free(Player* p);
+
 void ac_free(Player* p) {
+    ac_infer_free(p);
     for (auto a : p->act) if (a) cudaFree(a);
     p->act.clear();
     for (auto a : p->inf_act) if (a) cudaFree(a);
@@ -301,18 +304,88 @@ int ac_forward_backward(fi_learner* l, Player* p, const float* batch, int m, int
     return p->ac_tc ? ac_forward_backward_tc(l, p, batch, m, t) : ac_forward_backward_simt(l, p, batch, m, t);
 }
 
-int ac_infer_alloc(fi_learner* /*l*/, Player* p, size_t rows) {
+// ---------------------------------------------------------------- batched actor inference -----
+//  the forward kernels of the learner step on the published device snapshot of the weights:
+// obs_dev [rows,162] -> out_dev [rows,17]. Small batches (a few actors x a few rows) run the fp32 FFMA kernels; from
+// kInferTcRows rows on, the tensor-core forward of the step: 3xFP16 operand pairs, the same tcgen05 kernel and epilogue,
+// with two ping-pong activation buffers instead of five (nothing is kept for a backward pass).
+constexpr size_t kInferTcRows = 256;
+
+struct AcInfTc {
+    size_t rows_cap = 0;
+    HScale* hs = nullptr;                                // [kHsCount]
+    void *w_hi = nullptr, *w_lo = nullptr, *w1_hi = nullptr, *w1_lo = nullptr;
+    void *obs_hi = nullptr, *obs_lo = nullptr;           // [rows, 168]
+    void* act_hi[2] = {nullptr, nullptr};
+    void* act_lo[2] = {nullptr, nullptr};                // [rows, 512]
+};
+
+static void ac_inf_tc_free(AcInfTc* t) {
+    if (!t) return;
+    void* f[] = {t->hs, t->w_hi, t->w_lo, t->w1_hi, t->w1_lo, t->obs_hi, t->obs_lo, t->act_hi[0], t->act_hi[1], t->act_lo[0], t->act_lo[1]};
+    for (void* x : f) if (x) cudaFree(x);
+    delete t;
+}
+
+void ac_infer_free(Player* p) {
+    ac_inf_tc_free(static_cast<AcInfTc*>(p->inf_model_ws));
+    p->inf_model_ws = nullptr;
+}
+
+int ac_infer_alloc(fi_learner* l, Player* p, size_t rows) {
     for (auto a : p->inf_act) if (a) cudaFree(a);
     p->inf_act.assign(5, nullptr);
     for (int i = 0; i < 5; i++) FI_CUDA_OK(cudaMalloc((void**)&p->inf_act[i], rows * kHid * sizeof(float)));
+    ac_infer_free(p);
+    if (use_tc(l) && l->cfg.gemm_mode != FI_GEMM_TCGEN05 && rows >= kInferTcRows) {
+        AcInfTc* t = new AcInfTc();
+        p->inf_model_ws = t;
+        t->rows_cap = rows;
+        const size_t ab = ((l->arena_elems + 7) & ~(size_t)7) * 2, rb = rows * kHid * 2;
+        FI_CUDA_OK(cudaMalloc((void**)&t->hs, kHsCount * sizeof(HScale)));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w_hi, ab));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w_lo, ab));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_hi, (size_t)kHid * kObsLdH * 2));
+        FI_CUDA_OK(cudaMalloc((void**)&t->w1_lo, (size_t)kHid * kObsLdH * 2));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_hi, rows * kObsLdH * 2));
+        FI_CUDA_OK(cudaMalloc((void**)&t->obs_lo, rows * kObsLdH * 2));
+        for (int i = 0; i < 2; i++) {
+            FI_CUDA_OK(cudaMalloc((void**)&t->act_hi[i], rb));
+            FI_CUDA_OK(cudaMalloc((void**)&t->act_lo[i], rb));
+        }
+    }
     return FI_OK;
 }
 
-// Batched actor policy inference: the forward GEMM kernels on the
-// published device snapshot of the weights. obs_dev [rows,162] -> out_dev [rows,17].
-// Actor batches are small (tens to hundreds of rows), so this uses the fp32 FFMA kernels.
+static int ac_infer_tc(fi_learner* l, AcInfTc* t, const float* params, const float* obs_dev, int rows, float* out_dev, cudaStream_t st) {
+    const auto& T = l->tensors;
+    HScale* hs = t->hs;
+    const int arena_ld = (int)((l->arena_elems + 7) & ~(size_t)7);
+    auto off = [&](void* base, size_t elems) -> void* { return static_cast<char*>(base) + elems * 2; };
+    FI_TRY(launch_zero2(hs, kHsCount * sizeof(HScale), nullptr, 0, st));
+    FI_TRY(launch_amax(params, (int)l->arena_elems, 1, (int)l->arena_elems, hs + kHsW, st));
+    FI_TRY(launch_amax(obs_dev, kZDim, (size_t)rows, kZDim, hs + kHsObs, st));
+    FI_TRY(launch_split_h(params, (int)l->arena_elems, 1, (int)l->arena_elems, arena_ld, t->w_hi, t->w_lo, hs + kHsW, 1, st));
+    FI_TRY(launch_split_h(params + T[0].offset, kZDim, kHid, kZDim, kObsLdH, t->w1_hi, t->w1_lo, hs + kHsW, 0, st));
+    FI_TRY(launch_split_h(obs_dev, kZDim, (size_t)rows, kZDim, kObsLdH, t->obs_hi, t->obs_lo, hs + kHsObs, 1, st));
+    SplitMat x{t->obs_hi, t->obs_lo, kObsLdH, hs + kHsObs};
+    for (int layer = 0; layer < 5; layer++) {
+        const SplitMat w = layer == 0 ? SplitMat{t->w1_hi, t->w1_lo, kObsLdH, hs + kHsW}
+                                      : SplitMat{off(t->w_hi, T[2 * layer].offset), off(t->w_lo, T[2 * layer].offset), kHid, hs + kHsW};
+        const int cur = layer & 1;
+        const TcOut out{nullptr, 0, t->act_hi[cur], t->act_lo[cur], kHid, 0, nullptr, nullptr, kHid / 32, nullptr, hs + kHsAct0 + layer, hs + kHsW};
+        FI_TRY(launch_gemm_tc_split(0, rows, kHid, layer == 0 ? kZDim : kHid, x, w, out, params + T[2 * layer + 1].offset, 1, nullptr, 0, nullptr, 0, st));
+        x = SplitMat{t->act_hi[cur], t->act_lo[cur], kHid, hs + kHsAct0 + layer};
+    }
+    const SplitMat wh{off(t->w_hi, T[10].offset), off(t->w_lo, T[10].offset), kHid, hs + kHsW};
+    return launch_gemm_tc_split(0, rows, kHead, kHid, x, wh, TcOut{out_dev, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
+                                params + T[11].offset, 0, nullptr, 0, nullptr, 0, st);
+}
+
 int ac_infer(fi_learner* l, Player* p, const float* params, const float* obs_dev, size_t rows, float* out_dev,
              cudaStream_t stream) {
+    AcInfTc* t = static_cast<AcInfTc*>(p->inf_model_ws);
+    if (t && rows >= kInferTcRows && rows <= t->rows_cap) return ac_infer_tc(l, t, params, obs_dev, (int)rows, out_dev, stream);
     return ac_forward_simt(l, params, obs_dev, kZDim, (int)rows, p->inf_act.data(), out_dev, nullptr, 0, stream);
 }
 

@@ -118,14 +118,23 @@ int main(int argc, char** argv) {
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         size_t updates = 0;
         for (size_t p = 0; p < P.players; p++) updates += learner.iterationsDone(p);
+        uint64_t inf_calls = 0, inf_batches = 0;   // concurrent actors' requests are combined into few forwards per player
+        for (size_t p = 0; p < P.players; p++) {
+            uint64_t c = 0, b = 0;
+            fi_learner_infer_stats(learner.handle(), (int)p, &c, &b, nullptr);
+            inf_calls += c;
+            inf_batches += b;
+        }
         uint64_t vmin = ~0ull;
         for (size_t p = 0; p < P.players; p++) vmin = std::min<uint64_t>(vmin, learner.getModelManager()->getLatestVersion(p));
         printf("{\"harness\": \"freeimpala_gpu\", \"players\": %zu, \"agents\": %zu, \"batch_size\": %zu, \"entry_size\": %zu, "
                "\"learner_updates\": %zu, \"expected_updates\": %zu, \"seconds\": %.4f, \"updates_per_s\": %.2f, "
-               "\"transitions_per_s\": %.1f, \"min_model_version\": %llu, \"actor_inference_rows\": %llu, \"kernel_launches\": %llu}\n",
+               "\"transitions_per_s\": %.1f, \"min_model_version\": %llu, \"actor_inference_rows\": %llu, "
+               "\"actor_inference_calls\": %llu, \"actor_inference_forwards\": %llu, \"kernel_launches\": %llu}\n",
                P.players, P.agents, P.batch_size, P.entry_size, updates, learner_iterations * P.players, sec, updates / sec,
                updates * (double)P.batch_size * P.entry_size / sec, (unsigned long long)vmin,
-               (unsigned long long)inferences.load(), (unsigned long long)fi_kernel_launch_count());
+               (unsigned long long)inferences.load(), (unsigned long long)inf_calls, (unsigned long long)inf_batches,
+               (unsigned long long)fi_kernel_launch_count());
         return updates == learner_iterations * P.players ? 0 : 1;
     } catch (const std::exception& e) {
         fprintf(stderr, "freeimpala_gpu: %s\n", e.what());

@@ -288,6 +288,12 @@ class Learner:
         return values
 
     # ---- data parallelism ------------------------------------------------------------
+    def infer_stats(self, player_index: int) -> dict:
+        """Counters of the combining inference path: calls made, forwards run, rows served."""
+        c, b, r = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._lib.fi_learner_infer_stats(self._h, player_index, C.byref(c), C.byref(b), C.byref(r)), "fi_learner_infer_stats")
+        return {"calls": c.value, "batches": b.value, "rows": r.value}
+
     def dp_init(self, ids: bytes, rank: int, world_size: int) -> None:
         assert len(ids) == self.num_players * _lib.DP_ID_BYTES
         buf = C.create_string_buffer(ids, len(ids))

@@ -227,6 +227,10 @@ FI_API void* fi_learner_param_ptr(fi_learner* l, int player);
  * host observations [rows,162] -> logits [rows,16], values [rows] (actor-critic model), or
  * z [rows,T,162], x [rows,484] -> values [rows] (farmer model; logits may be NULL). */
 FI_API int fi_learner_infer(fi_learner* l, int player, const float* obs_or_z, const float* x, size_t rows, size_t t, float* logits, float* values);
+/* fi_learner_infer is thread-safe and COMBINING: requests of concurrent callers (the actors of one player) are packed into one
+ * host->device copy, one forward on the newest published weights and one device->host copy per batch. Counters since creation:
+ * calls made, forwards run, rows served (any may be NULL). No counterpart in the reference (the hook is a comment, agent.h:52-56). */
+FI_API int fi_learner_infer_stats(fi_learner* l, int player, uint64_t* calls, uint64_t* batches, uint64_t* rows);
 
 /* ---- model store: Model / ModelManager (data_structures.h:43-157, 310-481) ---- */
 FI_API size_t fi_model_bytes(const fi_learner* l);                                  /* blob size, fixed */

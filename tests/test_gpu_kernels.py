@@ -194,6 +194,53 @@ def test_ring_reserve_many_commit_many(fi, torch_cuda):
     ring.close()
 
 
+def test_ring_posted_receives_complete_out_of_order(fi, torch_cuda):
+    """Stand-in for the MPI receiver of freeimpala_mpi_async (cmd/freeimpala_mpi_async/main.cpp:283-297: NUM_SLOTS posted
+    MPI_Irecv's, MPI_Waitany, handle, repost) with the zero-copy producer API: every "receive" is
+    posted straight into a reserved pinned ring slot, the "network" (a pool of threads with random delays) completes them out
+    of order, and each completion commits its own ticket. The learner must see the trajectories in POSTING order, byte for
+    byte, whatever the completion order, across many ring wrap-arounds, while it consumes batches concurrently."""
+    import ctypes as C
+    import threading
+    cap, entry, m, total, posted_max = 16, 2, 4, 160, 8
+    ring = fi.SharedBuffer(entry, cap)
+    slot = ring.slot_bytes
+    rng = np.random.default_rng(11)
+    payload = rng.integers(0, 256, size=(total, slot), dtype=np.uint8)
+    delays = rng.random(total) * 2e-3
+    sem = threading.Semaphore(posted_max)           # at most posted_max receives outstanding, like NUM_SLOTS
+    done_order, lock = [], threading.Lock()
+
+    def complete(i, view, ticket):                  # the "network": fills the posted buffer some time later, then Waitany fires
+        import time
+        time.sleep(delays[i])
+        view[:] = payload[i]
+        with lock:
+            done_order.append(i)
+        assert ring.commit(ticket)
+        sem.release()
+
+    def receiver():                                 # posts receives in order; completions run on their own threads
+        ts = []
+        for i in range(total):
+            sem.acquire()
+            view, ticket = ring.reserve()           # blocks while the ring is full: back-pressure on the posting side
+            t = threading.Thread(target=complete, args=(i, view, ticket))
+            t.start()
+            ts.append(t)
+        for t in ts:
+            t.join()
+
+    rx = threading.Thread(target=receiver)
+    rx.start()
+    got = [ring.readBatch(m).to_host() for _ in range(total // m)]
+    rx.join(timeout=60)
+    assert not rx.is_alive()
+    assert done_order != sorted(done_order), "the completions were meant to be out of order"
+    assert np.array_equal(np.concatenate(got), payload)
+    ring.close()
+
+
 # ------------------------------------------------------------------------------- Adam
 @pytest.mark.parametrize("kind,n", [("adam", 1514497), ("adamw", 10007), ("sgd", 4099), ("adam", 3), ("adam", 1142801)])
 def test_fused_optimizer_bit_exact_vs_f32_oracle(fi, oracle, torch_cuda, kind, n):

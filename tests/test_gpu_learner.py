@@ -221,6 +221,51 @@ def test_batched_actor_inference_vs_oracle(fi, oracle):
     L.close()
 
 
+@pytest.mark.parametrize("gemm_mode", ["simt", "tcgen05", "tcgen05_f16", "auto"])
+def test_concurrent_actor_inference_is_combined_and_matches_oracle(fi, oracle, gemm_mode):
+    """64 actors of one player ask for the policy at the same time (Agent::simulateGame's hook, agent.h:52-56): their
+    requests are combined into a few forwards on the published weights (fi_learner_infer_stats), every caller gets its own
+    rows, and the rows match the float64 oracle. A single large request (1000 rows) takes the tensor-core forward in the
+    fp16 modes; it must meet the same tolerance."""
+    import threading
+    params = U.ac_params(23)
+    L = _ac_learner(fi, 4, 5, gemm_mode=gemm_mode)
+    L.set_params(0, params)
+    O = oracle.actor_critic(params)
+    rng = np.random.default_rng(7)
+    actors, rounds = 64, 6
+    obs = [rng.standard_normal((rounds, 1 + a % 5, 162)).astype(np.float32) for a in range(actors)]   # 1..5 rows per call
+    got = [[None] * rounds for _ in range(actors)]
+    barrier = threading.Barrier(actors)
+
+    def actor(a):
+        for r in range(rounds):
+            barrier.wait()                      # all actors of a round call together
+            got[a][r] = L.infer(0, obs[a][r])
+
+    ts = [threading.Thread(target=actor, args=(a,)) for a in range(actors)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts)
+    for a in range(actors):
+        for r in range(rounds):
+            wl, wv = O.forward(obs[a][r])
+            logits, values = got[a][r]
+            scale = max(np.abs(wl).max(), np.abs(wv).max())      # a call carries 1-5 rows: one scale for the 17 head outputs
+            assert np.abs(logits - wl).max() < TOL * scale and np.abs(values - wv).max() < TOL * scale, (a, r)
+    st = L.infer_stats(0)
+    assert st["calls"] == actors * rounds and st["rows"] == sum(o.shape[0] * o.shape[1] for o in obs)
+    print(f"[{gemm_mode}] {st['calls']} concurrent inference calls served by {st['batches']} forwards")
+    assert st["batches"] <= st["calls"] // 4    # combining: on average at least 4 callers per forward
+    big = rng.standard_normal((1000, 162)).astype(np.float32)
+    logits, values = L.infer(0, big)
+    wl, wv = O.forward(big)
+    assert U.rel_max(logits, wl) < TOL and U.rel_max(values, wv) < TOL
+    L.close()
+
+
 def test_create_rejects_bad_config(fi):
     with pytest.raises(fi.FiError):
         fi.Learner(1, 2, 5, 3)                                  # M > B (validateParameters)
@@ -392,3 +437,40 @@ def test_full_size_step_vs_oracle(fi, oracle):
     O.opt_step()
     assert U.rel_l2(L.get_params(0), O.params()) < TOL
     L.close()
+
+
+@pytest.mark.parametrize("model", ["mlp_actor_critic", "farmer_lstm"])
+def test_graph_replayed_steps_equal_stream_launched_steps(fi, model, monkeypatch):
+    """fi_learner_step replays the step as one CUDA graph from the third step on (only the optimiser node is re-parameterised:
+    step count, snapshot and loss slots). Ten steps through the graph path must give the same bits as ten steps enqueued launch
+    by launch (FI_GRAPH=0 is read once per process, so the reference run uses forward_backward + apply_update, which never
+    use the graph), with the batch alternating between two buffers so that the graph is re-captured on the way."""
+    m, t = 16, 20
+    farmer = model == "farmer_lstm"
+    mk = (lambda: _farmer_learner(fi, m, t, gemm_mode="auto")) if farmer else (lambda: _ac_learner(fi, m, t, gemm_mode="auto"))
+    A, B = mk(), mk()
+    params = U.farmer_params(3) if farmer else U.ac_params(3)
+    for X in (A, B):
+        X.set_params(0, params)
+    slots = []
+    for s in range(3):
+        if farmer:
+            slots.append(po.pack_farmer_slots(*U.farmer_batch(500 + s, m, t)))
+        else:
+            slots.append(po.pack_vtrace_slots(*U.vtrace_batch(500 + s, m, t)))
+    n0 = fi.kernel_launch_count()
+    ring = A.getSharedBuffers()[0]
+    for s in range(10):
+        if s % 4 == 3:                       # through the ring now and then: another batch buffer -> re-capture
+            assert ring.write_many(slots[s % 3]) == m
+            A.trainModel(0, ring.readBatch(m))
+        else:
+            A.trainModel(0, A.stage_batch(0, slots[s % 3]))
+        B.forward_backward(0, B.stage_batch(0, slots[s % 3]))
+        B.apply_update(0)
+        np.testing.assert_allclose(A.last_losses(0), B.last_losses(0), rtol=1e-6)   # loss sums: double atomics, order varies
+    assert np.array_equal(A.get_params(0), B.get_params(0))
+    assert A.getModelManager().getLatestVersion(0) == 11 and A.steps_done(0) == 10
+    assert fi.kernel_launch_count() - n0 > 200      # graph launches are counted kernel by kernel
+    A.close()
+    B.close()

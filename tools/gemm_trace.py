@@ -25,6 +25,7 @@ NAMES = {1: "P wait empty", 2: "P issue loads", 10: "I wait main_empty", 11: "I 
 
 def main():
     os.environ.setdefault("FI_TC_TRACE", "0,512,512")
+    os.environ["FI_GRAPH"] = "0"   # the trace buffer is (re)set with a legacy-stream memset at every traced launch
     import bench
     import freeimpala_b200 as fi
     import torch
