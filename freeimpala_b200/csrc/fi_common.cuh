@@ -94,6 +94,15 @@ inline ProfState& prof() {
 class LaunchScope {
 public:
     LaunchScope(const char* name, cudaStream_t st, double work, int unit) : name_(name), st_(st) {
+        // A non-sticky error left behind by an earlier runtime call of this thread (seen: "invalid device function" after
+        // NCCL's communicator set-up in a 2-GPU process) must not be blamed on the launch that follows: take it out of the
+        // last-error slot first, and say so once. Sticky errors (a faulted kernel) survive this and are still reported.
+        const cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess) {
+            static std::atomic<bool> said{false};
+            if (!said.exchange(true))
+                fprintf(stderr, "[freeimpala_b200] note: cleared a stale CUDA error before launching %s: %s\n", name, cudaGetErrorString(stale));
+        }
         ProfState& p = prof();
         if (!p.on.load(std::memory_order_relaxed)) return;
         std::lock_guard<std::mutex> g(p.mu);

@@ -31,11 +31,10 @@ int launch_gemm(int mode, int trans, int m, int n, int k, const float* a, int ld
         return launch_gemm_h(trans, m, n, k, a, lda, b, ldb, c, ldc, bias, relu, mask, ldmask, workspace, workspace_bytes, stream);
     }
     if (mode != FI_GEMM_SIMT) {
-        // AUTO: the tensor-core path pays two split pre-passes (and a split-K reduction) for plain fp32 operands: ~25 us of
-        // launches around the product. The fp32 FFMA kernel runs ~38 TFLOP/s, so below ~2 GFLOP it finishes first: the
-        // FarmerLstm dense stack at batch 1024 (0.5-0.6 GFLOP per layer, 30 split launches = 7 % of the step in round 1)
-        // stays on it; the [rows*T]-sized LSTM products (17-27 GFLOP) take the tensor cores.
-        const bool big = 2.0 * (double)m * (double)n * (double)k >= 2e9;
+        // AUTO: the tensor-core path pays a split pre-pass for plain fp32 operands; use it from ~64 MFLOP up. (Measured in
+        // round 2: sending the FarmerLstm dense stack at batch 1024 -- 0.5 GFLOP per product -- to the fp32 FFMA kernel instead
+        // costs 56 us per product against ~25 us for split + tensor-core product: the FFMA kernel is inefficient at m = 1024.)
+        const bool big = 2.0 * (double)m * (double)n * (double)k >= 64e6;
         if ((mode == FI_GEMM_TCGEN05 || big) && gemm_tc_supported(trans, m, n, k, a, lda, b, ldb, c, ldc) &&
             (mode == FI_GEMM_TCGEN05 || (workspace && workspace_bytes >= gemm_tc_workspace_bytes(trans, m, n, k))))
             return launch_gemm_tc(trans, m, n, k, a, lda, b, ldb, c, ldc, bias, relu, mask, ldmask, workspace,

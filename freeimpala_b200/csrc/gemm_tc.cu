@@ -1173,18 +1173,18 @@ static int make_map_uncached(CUtensorMap* map, const void* base, uint64_t inner,
     return FI_OK;
 }
 
-// FI_TC_TRACE="<trans>,<min n>,<min k>": launches of that operand-major combination with n >= min n and k >= min k log their
+// FI_TC_TRACE="<trans>,<min n>,<min k>[,<max k>]": launches of that operand-major combination with n >= min n and min k <= k <= max k log their
 // pipeline events into a device buffer (each matching launch starts a fresh log); fi_debug_tc_trace copies it out.
 static unsigned long long* g_tc_trace = nullptr;
 static unsigned long long* tc_trace_buffer(int trans, int /*m*/, int n, int k) {
-    struct Filter { int on, trans, n, k; };
+    struct Filter { int on, trans, n, k, kmax; };
     static const Filter f = [] {
         const char* e = getenv("FI_TC_TRACE");
-        Filter r{0, 0, 0, 0};
-        if (e) r.on = sscanf(e, "%d,%d,%d", &r.trans, &r.n, &r.k) >= 1;
+        Filter r{0, 0, 0, 0, 1 << 30};
+        if (e) r.on = sscanf(e, "%d,%d,%d,%d", &r.trans, &r.n, &r.k, &r.kmax) >= 1;
         return r;
     }();
-    if (!f.on || trans != f.trans || n < f.n || k < f.k) return nullptr;
+    if (!f.on || trans != f.trans || n < f.n || k < f.k || k > f.kmax) return nullptr;
     const size_t bytes = (size_t)kTraceCtas * kTraceRoles * kTraceCap * sizeof(unsigned long long);
     if (!g_tc_trace && cudaMalloc((void**)&g_tc_trace, bytes) != cudaSuccess) return nullptr;
     cudaMemset(g_tc_trace, 0, bytes);   // legacy-stream memset: diagnostics only

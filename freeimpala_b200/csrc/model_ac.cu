@@ -15,7 +15,9 @@
 namespace fi {
 
 constexpr int kObsLd = 164;     // 162 observation words padded to a 16-byte multiple (TMA row stride), 3xTF32 format
-constexpr int kObsLdH = 168;    // the same for fp16 elements
+constexpr int kObsLdH = 192;    // fp16 elements: 162 padded to 192 = three whole 128-byte lines per row, so that every TMA box row
+                                // (one 64-element k-block of one observation) is ONE aligned line; with the minimal 168 (336-byte
+                                // rows) each box row straddled two lines and layer 1's operand loads took 5800 clocks (profiles/r2_gemm_trace.md)
 constexpr int kDheadLd = 32;    // 17 head gradients padded to one TF32 k-block
 
 // HScale slots of the 3xFP16 format (one per split tensor)

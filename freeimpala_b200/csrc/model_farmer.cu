@@ -44,7 +44,7 @@ struct FarmerWs {
     void *hp_hi = nullptr, *hp_lo = nullptr;       // [rows*T, 128]
     void* split_ws = nullptr; size_t split_ws_bytes = 0;
 };
-constexpr int kObsLdH = 168;   // 162 observation words padded to a 16-byte multiple of fp16
+constexpr int kObsLdH = 192;   // 162 observation words padded to three whole 128-byte lines of fp16 (see model_ac.cu)
 enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
