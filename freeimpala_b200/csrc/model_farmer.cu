@@ -49,6 +49,17 @@ enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// Two fp32 FMAs in one instruction (sm_100 FFMA2; bit-identical to two fmaf's). With b = {w, w} ptxas emits the scalar-broadcast
+// form (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2), so a row pair of the recurrent products costs one issue slot instead of two.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 // out[k][j] = in[j][k] for the [512,128] recurrent weight
 __global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restrict__ wt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,23 +119,27 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         wreg[k] = __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)(kLstmSmemK + k) * kG4 + j0));
     __syncthreads();
     for (int s = 0; s < t; s++) {
-        float acc[kLstmRows][2];
+        float2 acc2[kLstmRows / 2][2];   // [row pair][column]: .x = row 2 rp, .y = row 2 rp + 1
         float2 gx[kLstmRows];
 #pragma unroll
         for (int r = 0; r < kLstmRows; r++) {
             gx[r] = make_float2(0.f, 0.f);
             if (r < nrows) gx[r] = *reinterpret_cast<const float2*>(gates + ((size_t)(b0 + r) * t + s) * kG4 + j0);
-            acc[r][0] = bias.x;
-            acc[r][1] = bias.y;
+        }
+#pragma unroll
+        for (int rp = 0; rp < kLstmRows / 2; rp++) {
+            acc2[rp][0] = make_float2(bias.x, bias.x);
+            acc2[rp][1] = make_float2(bias.y, bias.y);
         }
         auto fma_k = [&](int k, float2 w) {
             const float4 h0 = *reinterpret_cast<const float4*>(hs + k * kLstmRows);
             const float4 h1 = *reinterpret_cast<const float4*>(hs + k * kLstmRows + 4);
-            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const float2 hp[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
+            const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
 #pragma unroll
-            for (int r = 0; r < kLstmRows; r++) {
-                acc[r][0] = fmaf(hv[r], w.x, acc[r][0]);
-                acc[r][1] = fmaf(hv[r], w.y, acc[r][1]);
+            for (int rp = 0; rp < kLstmRows / 2; rp++) {   // 8 FFMA2 = the 16 FMAs of this k
+                acc2[rp][0] = ffma2(hp[rp], wx, acc2[rp][0]);
+                acc2[rp][1] = ffma2(hp[rp], wy, acc2[rp][1]);
             }
         };
 #pragma unroll 8
@@ -133,11 +148,9 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         for (int k = kLstmSmemK; k < kLstmH; k++) fma_k(k, wreg[k - kLstmSmemK]);
 #pragma unroll
         for (int r = 0; r < kLstmRows; r++) {
-            acc[r][0] += gx[r].x;
-            acc[r][1] += gx[r].y;
+            const float a0 = (r & 1) ? acc2[r >> 1][0].y : acc2[r >> 1][0].x, a1 = (r & 1) ? acc2[r >> 1][1].y : acc2[r >> 1][1].x;
+            *reinterpret_cast<float2*>(ps + r * kG4 + j0) = make_float2(a0 + gx[r].x, a1 + gx[r].y);
         }
-#pragma unroll
-        for (int r = 0; r < kLstmRows; r++) *reinterpret_cast<float2*>(ps + r * kG4 + j0) = make_float2(acc[r][0], acc[r][1]);
         __syncthreads();
         // (row, unit) pairs: 8 * 128 = 1024 over 256 threads
         for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
@@ -228,17 +241,18 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
         }
         __syncthreads();
         if (s > 0) {  // dh_{s-1}[r][k] = sum_j dG[r][j] W_hh[j][k]
-            float acc[kLstmRows][2];
+            float2 acc2[kLstmRows / 2][2];   // [row pair][column]
 #pragma unroll
-            for (int r = 0; r < kLstmRows; r++) acc[r][0] = acc[r][1] = 0.f;
+            for (int rp = 0; rp < kLstmRows / 2; rp++) acc2[rp][0] = acc2[rp][1] = make_float2(0.f, 0.f);
             auto fma_j = [&](int j, float2 w) {
                 const float4 g0 = *reinterpret_cast<const float4*>(dgs + j * kLstmRows);
                 const float4 g1 = *reinterpret_cast<const float4*>(dgs + j * kLstmRows + 4);
-                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float2 gp[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+                const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
 #pragma unroll
-                for (int r = 0; r < kLstmRows; r++) {
-                    acc[r][0] = fmaf(gv[r], w.x, acc[r][0]);
-                    acc[r][1] = fmaf(gv[r], w.y, acc[r][1]);
+                for (int rp = 0; rp < kLstmRows / 2; rp++) {
+                    acc2[rp][0] = ffma2(gp[rp], wx, acc2[rp][0]);
+                    acc2[rp][1] = ffma2(gp[rp], wy, acc2[rp][1]);
                 }
             };
 #pragma unroll 8
@@ -247,7 +261,8 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
             for (int jj = 0; jj < 64; jj++) fma_j(q * kLstmH + 64 + jj, wreg[jj]);
 #pragma unroll
             for (int r = 0; r < kLstmRows; r++)
-                *reinterpret_cast<float2*>(part + (q * kLstmRows + r) * kLstmH + k0) = make_float2(acc[r][0], acc[r][1]);
+                *reinterpret_cast<float2*>(part + (q * kLstmRows + r) * kLstmH + k0) =
+                    make_float2((r & 1) ? acc2[r >> 1][0].y : acc2[r >> 1][0].x, (r & 1) ? acc2[r >> 1][1].y : acc2[r >> 1][1].x);
             __syncthreads();
             for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads)
                 dh[i] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
