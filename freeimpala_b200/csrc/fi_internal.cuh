@@ -106,6 +106,10 @@ int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_o
 int launch_amax(const float* x, int ld_in, size_t rows, int cols, HScale* hs, cudaStream_t st);
 int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, int write_scale,
                    cudaStream_t st);
+// amax + split in one cooperative launch (row matrices; hs->amax must be zero on entry; publishes scale / inv / bound)
+int launch_amax_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, cudaStream_t st);
+int launch_amax_split_params(const float* p, int n, int ld_flat, void* hi, void* lo, const float* w, int w_rows, int w_cols, int ld2,
+                             void* hi2, void* lo2, HScale* hs, cudaStream_t st);
 int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,
                          const float* mask, int ldmask, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_tc_split_workspace_bytes(int trans, int m, int n, int k);
