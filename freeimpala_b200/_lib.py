@@ -50,6 +50,7 @@ SIGNATURES = {
     "fi_prof_enable": (None, [c_int]),
     "fi_prof_collect": (c_int, [C.POINTER(FiProfEntry), c_int]),
     "fi_debug_tc_trace": (c_int, [_P, c_size_t]),
+    "fi_debug_set_lstm_tc": (None, [c_int]),
     "fi_ring_create": (_P, [c_int, c_size_t, c_size_t]),
     "fi_ring_destroy": (None, [_P]),
     "fi_ring_write": (c_int, [_P, _P, c_size_t]),

@@ -99,7 +99,32 @@ struct TcOut {
     const HScale* bias_hs = nullptr;         // fp16 format: a tensor whose amax bounds |bias| (the parameter arena)
     int* deferred_splits = nullptr;          // non-null: leave the split-K slabs in the workspace ([splits][m*n], the output's
                                              // layout) and report their number here (1: the product wrote `c` itself)
+    int step_t = 0, step_nblk = 0;           // step_t > 0: c is the blocked gate array of the recurrent kernels (step_block_offset)
 };
+
+// ---- blocked per-step arrays of the recurrent kernels (lstm_tc.cu) ----------------------------------------------------------
+// gates [(b, s), 512] and c [(b, s), 128] are kept so that what ONE CTA touches per step is contiguous: blocks of
+// [4 gates][64 batch rows][16 units] fp32 (16 KB) / [64 batch rows][16 units] (4 KB), ordered [step][64-row block][unit block].
+// Inside a block a row is 64 bytes and its four 16-byte chunks are XOR-swizzled with bits 1..2 of the row, so that threads
+// that own one batch row each (a TMEM lane) read and write shared-memory copies of the block without bank conflicts.
+constexpr int kStepBlockRows = 64, kStepBlockUnits = 16;
+constexpr int kStepGateBlock = 4 * kStepBlockRows * kStepBlockUnits;   // floats per gate block
+constexpr int kStepCellBlock = kStepBlockRows * kStepBlockUnits;       // floats per c block
+__host__ __device__ __forceinline__ size_t step_block_index(int s, int b, int unit, int nblk) {
+    return ((size_t)s * nblk + (b >> 6)) * 8 + (unit >> 4);
+}
+__host__ __device__ __forceinline__ int step_row_offset(int b, int unit) {   // floats, inside a [64 rows][16 units] tile
+    const int r = b & 63, uu = unit & 15;
+    return r * 16 + (((uu >> 2) ^ ((r >> 1) & 3)) << 2) + (uu & 3);
+}
+// gate column col = gate * 128 + unit of batch row b at step s
+__host__ __device__ __forceinline__ size_t step_block_offset(int s, int b, int col, int nblk) {
+    const int gate = col >> 7, unit = col & 127;
+    return step_block_index(s, b, unit, nblk) * kStepGateBlock + gate * kStepCellBlock + step_row_offset(b, unit);
+}
+__host__ __device__ __forceinline__ size_t step_cell_offset(int s, int b, int unit, int nblk) {
+    return step_block_index(s, b, unit, nblk) * kStepCellBlock + step_row_offset(b, unit);
+}
 int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st);
 // fp16 format pre-passes: amax accumulates max |x| into hs->amax; split derives the scale from hs->amax (which must
 // bound the matrix) and writes hi / lo' with columns [cols, ld_out) zero-filled. write_scale: publish scale/inv in *hs.
@@ -108,6 +133,14 @@ int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out,
                    cudaStream_t st);
 // amax + split in one cooperative launch (row matrices; hs->amax must be zero on entry; publishes scale / inv / bound)
 int launch_amax_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, cudaStream_t st);
+// lstm_tc.cu: the FarmerLstm recurrence on tcgen05 (clusters of 8 CTAs per 128 batch rows, exchange through DSMEM)
+bool lstm_tc_enabled();   // FI_LSTM_TC=0 keeps the fp32 FFMA kernels of model_farmer.cu
+int launch_lstm_forward_tc(float* gates, const float* whh, const float* b_hh, int m, int t, void* hp_hi, void* hp_lo, HScale* hp_hs,
+                           float* cst, float* feat, int ldfeat, cudaStream_t st);
+// gates / cst: blocked arrays (step_block_offset below), rows padded to 64. bias_part: [ceil(m / 64), 512] scratch.
+int launch_lstm_backward_tc(float* gates, const float* whh, const float* cst, const float* dfeat, int ldf, int m, int t, HScale* dg_hs,
+                            float* bias_part, float* g_bih, float* g_bhh, cudaStream_t st);
+int launch_lstm_split_gates(const float* gates, int m, int t, void* hi, void* lo, HScale* hs, cudaStream_t st);
 int launch_amax_split_params(const float* p, int n, int ld_flat, void* hi, void* lo, const float* w, int w_rows, int w_cols, int ld2,
                              void* hi2, void* lo2, HScale* hs, cudaStream_t st);
 int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b, TcOut out, const float* bias, int relu,

@@ -46,6 +46,7 @@
 #include <unordered_map>
 
 #include "fi_internal.cuh"
+#include "tc_ptx.cuh"
 
 namespace fi {
 
@@ -74,6 +75,8 @@ struct TcEpilogue {
     int tma_split;       // c_hi / c_lo are written with TMA stores (map_c_hi / map_c_lo are valid)
     float* colsum_out;   // [4 * num_m_blocks, n]: column sums of the output over each warp's 32 rows (bias gradient), or null
     size_t split_stride; // elements between split-K slabs of c
+    int step_t;          // > 0: c is the recurrent kernels' blocked gate array (lstm_tc.cu, step_block_offset): row = b * step_t + s
+    int step_nblk;       //      blocks of 64 batch rows
     // 3xFP16 format only
     const HScale* a_hs;  // operand scales: the accumulator is (A * sa)(B * sb), multiplied by inv_a * inv_b on the way out
     const HScale* b_hs;
@@ -103,205 +106,6 @@ struct TraceLog {
     }
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        // a pipeline bug must surface as a launch error, never as a hung GPU (a failed try_wait returns after the hardware's
-        // time limit, ~10 us: 2^20 of them are ~10 s, far beyond any legitimate wait)
-        if (!done && ++spins > (1u << 20)) __trap();
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// one full 32-byte sector per lane, no L1 allocation (every byte is written once)
-__device__ __forceinline__ void st_global_v8u(void* p, const uint32_t* v) {
-    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// ---- CTA-pair (cta_group::2) variants ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-// Arrive on a barrier of another CTA of the cluster. Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier
-// does: what the arrival publishes here is the completion of tcgen05.ld's, ordered by tcgen05.fence::before_thread_sync.
-// (Round 1 used .release.cluster: a cluster-scope release is a full memory barrier -- 2000-3500 clocks per chunk on every
-// promotion warp while the TMA keeps the memory system busy, which is what made the CTA-pair mode lose; profiles/r2_gemm_trace.md.)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier
-// (peer bit of the barrier address cleared, as cute::SM100_TMA_2SM_LOAD_2D does)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                 uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// One elected lane of a converged warp (elect.sync): the role loops of the producer and issuer warps run warp-uniformly --
-// every operand of the TMA / tcgen05 instructions then lives in uniform registers -- and only the asynchronous
-// instructions themselves sit under this predicate. (Round 1 ran those loops inside `if (lane == 0)`: the compiler had to
-// move the five operands of every UTCHMMA from vector to uniform registers with an ELECT + R2UR.BROADCAST waterfall loop,
-// ~60 clocks per MMA: the issuer needed ~970 clocks per k-block for 768 clocks of tensor-core work; profiles/r2_gemm_trace.md.)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= 1ull << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms)
-    return d;
-}
-// tcgen05 instruction descriptor: D fp32, A/B tf32 (format 2) or fp16 (format 0), dense (cute::UMMA::InstrDescriptor bit layout).
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major, int half) {
-    const uint32_t fmt = half ? 0u : 2u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// Scale of a 3xFP16 tensor bounded by `bound`: the power of two that puts the bound in (2^13, 2^14], a factor 4 under the
-// fp16 maximum (the bound is computed in fp32 and the data it bounds carry fp32 rounding). hi and lo' then resolve
-// 2^-36 absolutely and 2^-22 relatively, i.e. tensors whose true maximum sits up to ~2^27 below the bound keep fp32-level
-// accuracy in the norm-wise sense that matters for a dot product.
-__host__ __device__ __forceinline__ float hscale_from_bound(float bound) {
-    if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
-    int ex;
-    frexpf(bound, &ex);                 // bound = f * 2^ex, f in [0.5, 1)
-    int e = 14 - ex;
-    e = e > 60 ? 60 : (e < -60 ? -60 : e);   // products of two scales (and bias * scale_a * scale_b) stay finite
-    return ldexpf(1.f, e);
-}
 // column sums of a 32 x 32 block held one row per lane (x[i] = column i of this lane's row) by recursive halving: after the
 // step with offset o a lane keeps the half of its columns selected by its bit o, summed with its partner's; 31 shuffles, and
 // lane j returns the sum of column j.
@@ -922,6 +726,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const bool col_ok = col < sh.n;
                 const float bias = (ep.bias && col_ok) ? __ldg(ep.bias + col) : 0.f;
                 float* pc = cplain ? cplain + (size_t)rbase * ep.ldc + col : nullptr;
+                int blk_b = 0, blk_s = 0;   // blocked gate array: batch row and step of row rbase
+                if (ep.step_t > 0) { blk_b = rbase / ep.step_t; blk_s = rbase - blk_b * ep.step_t; }
                 float* ph = (!H && ep.c_hi) ? static_cast<float*>(ep.c_hi) + (size_t)rbase * ep.ldc_split + col : nullptr;
                 float* pl = (!H && ep.c_hi) ? static_cast<float*>(ep.c_lo) + (size_t)rbase * ep.ldc_split + col : nullptr;
                 const float* pm = ep.mask ? ep.mask + (size_t)rbase * ep.ldmask + col : nullptr;
@@ -944,7 +750,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             const uint32_t w32 = __ballot_sync(0xFFFFFFFFu, col_ok && t > 0.f);
                             if (lane == rr0 + u) myword = w32;
                         }
-                        if (col_ok && rr0 + u < rows_here) {
+                        if (ep.step_t > 0) {
+                            if (col_ok && rr0 + u < rows_here) cplain[step_block_offset(blk_s, blk_b, col, ep.step_nblk)] = t;
+                            if (++blk_s == ep.step_t) { blk_s = 0; blk_b++; }
+                        } else if (col_ok && rr0 + u < rows_here) {
                             if (pc) pc[(size_t)u * ep.ldc] = t;
                             if (ph) {
                                 const float h = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);
@@ -1295,6 +1104,27 @@ static int make_map_uncached(CUtensorMap* map, const void* base, uint64_t inner,
     return FI_OK;
 }
 
+// A [rows b][steps t][cols] array (row (b, s) at (b * t + s) * cols) as the 3-D tensor (cols, t, b) with boxes of
+// (box_cols, 1, box_rows): one box = the columns [c0, c0 + box_cols) of step s for box_rows consecutive batch rows -- what one CTA
+// of the recurrent kernels (lstm_tc.cu) loads or stores per step. swizzle_bytes = box_cols * elem_bytes: 32 or 64.
+int make_step_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t t, uint64_t rows, uint32_t box_cols,
+                         uint32_t box_rows, int swizzle_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (cols * elem_bytes) % 16 || (int)box_cols * elem_bytes != swizzle_bytes)
+        return set_error(FI_ERR_ARG, "step tensor map: base / row stride must be 16-byte aligned and the box row must span the swizzle");
+    cuuint64_t dims[3] = {cols, t, rows};
+    cuuint64_t strides[2] = {cols * (uint64_t)elem_bytes, t * cols * (uint64_t)elem_bytes};
+    cuuint32_t box[3] = {box_cols, 1, box_rows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FI_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return FI_OK;
+}
+
 // FI_TC_TRACE="<trans>,<min n>,<min k>[,<max k>]": launches of that operand-major combination with n >= min n and min k <= k <= max k log their
 // pipeline events into a device buffer (each matching launch starts a fresh log); fi_debug_tc_trace copies it out.
 static unsigned long long* g_tc_trace = nullptr;
@@ -1416,6 +1246,9 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     ep.bias = bias; ep.relu = relu; ep.mask = mask; ep.ldmask = ldmask; ep.transpose_out = out.transpose; ep.split_stride = 0;
     ep.mask_bits = out.mask_bits_in; ep.mask_bits_out = out.mask_bits_out; ep.mask_ldw = out.mask_ldw;
     ep.colsum_out = out.colsum_out;
+    ep.step_t = out.step_t; ep.step_nblk = out.step_nblk;
+    if (out.step_t > 0 && (out.c_hi || out.transpose || !out.c || relu || mask || out.mask_bits_in || out.mask_bits_out || n != 512 || m % out.step_t))
+        return set_error(FI_ERR_ARG, "tcgen05 GEMM: the blocked gate-array output is a plain fp32 [b * t + s, 512] product");
     ep.a_hs = a.hs; ep.b_hs = b.hs; ep.bias_hs = bias ? out.bias_hs : nullptr; ep.out_hs = out.c_hi ? out.out_hs : nullptr;
     if (half && out.c_hi && (!out.out_hs || (bias && !out.bias_hs) || bn != 128))
         return set_error(FI_ERR_ARG, "tcgen05 GEMM (fp16 format): a split output needs n > 64, its HScale and a bound for the bias");
@@ -1424,7 +1257,8 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
         return set_error(FI_ERR_ARG, "tcgen05 GEMM: a bit mask excludes bias/ReLU and needs 16-byte aligned rows");
     if (sh.num_splits > 1) {
         const size_t need = (size_t)sh.num_splits * m * n * sizeof(float);
-        if (!workspace || workspace_bytes < need || bias || relu || mask || out.c_hi || !out.c || out.mask_bits_in || out.mask_bits_out) {
+        if (!workspace || workspace_bytes < need || bias || relu || mask || out.c_hi || !out.c || out.mask_bits_in || out.mask_bits_out ||
+            out.step_t > 0) {
             sh.num_splits = 1;  // no room for partials (or an epilogue is requested): one split per tile
         } else {
             ep.c = static_cast<float*>(workspace);

@@ -43,6 +43,7 @@ struct FarmerWs {
     void *dg_hi = nullptr, *dg_lo = nullptr;       // [rows*T, 512]
     void *hp_hi = nullptr, *hp_lo = nullptr;       // [rows*T, 128]
     void* split_ws = nullptr; size_t split_ws_bytes = 0;
+    float* bias_part = nullptr;                    // [ceil(rows / 64), 512]: per-cluster bias-gradient partials of the tensor-core BPTT
 };
 constexpr int kObsLdH = 192;   // 162 observation words padded to three whole 128-byte lines of fp16 (see model_ac.cu)
 enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
@@ -305,7 +306,7 @@ static void ws_release(FarmerWs* w) {
         if (p) cudaFree(p);
     if (w->gemm_ws) cudaFree(w->gemm_ws);
     if (w->colsum_ws) cudaFree(w->colsum_ws);
-    void* h[] = {w->hs, w->obs_hi, w->obs_lo, w->wih_hi, w->wih_lo, w->dg_hi, w->dg_lo, w->hp_hi, w->hp_lo, w->split_ws};
+    void* h[] = {w->hs, w->obs_hi, w->obs_lo, w->wih_hi, w->wih_lo, w->dg_hi, w->dg_lo, w->hp_hi, w->hp_lo, w->split_ws, w->bias_part};
     for (void* p : h)
         if (p) cudaFree(p);
     delete w;
@@ -317,14 +318,19 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
     w->rows = rows;
     w->t = t;
     const size_t rt = rows * t;
-    FI_CUDA_OK(cudaMalloc((void**)&w->gates, rt * kG4 * sizeof(float)));
+    // the tensor-core recurrence keeps gates and c in 64-row blocks (fi_internal.cuh): room for the padded rows, zeroed once so
+    // that what the padding rows carry stays finite
+    const size_t rt_pad = ((rows + kStepBlockRows - 1) / kStepBlockRows) * kStepBlockRows * t;
+    FI_CUDA_OK(cudaMalloc((void**)&w->gates, rt_pad * kG4 * sizeof(float)));
+    FI_CUDA_OK(cudaMemset(w->gates, 0, rt_pad * kG4 * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&w->whh_t, (size_t)kG4 * kLstmH * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&w->feat, rows * kFeat * sizeof(float)));
     FI_CUDA_OK(cudaMalloc((void**)&w->y, rows * sizeof(float)));
     for (int i = 0; i < 5; i++) FI_CUDA_OK(cudaMalloc((void**)&w->act[i], rows * kHid * sizeof(float)));
     if (training) {
         FI_CUDA_OK(cudaMalloc((void**)&w->hprev, rt * kLstmH * sizeof(float)));
-        FI_CUDA_OK(cudaMalloc((void**)&w->cst, rt * kLstmH * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->cst, rt_pad * kLstmH * sizeof(float)));
+        FI_CUDA_OK(cudaMemset(w->cst, 0, rt_pad * kLstmH * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->dy, rows * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->target, rows * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->d_a, rows * kFeat * sizeof(float)));
@@ -360,6 +366,7 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
             FI_CUDA_OK(cudaMalloc(&w->dg_lo, rt * kG4 * 2));
             FI_CUDA_OK(cudaMalloc(&w->hp_hi, rt * kLstmH * 2));
             FI_CUDA_OK(cudaMalloc(&w->hp_lo, rt * kLstmH * 2));
+            FI_CUDA_OK(cudaMalloc((void**)&w->bias_part, (rt_pad / t / kStepBlockRows) * kG4 * sizeof(float)));
             size_t sw = gemm_tc_split_workspace_bytes(2, kG4, kZDim, (int)rt);
             const size_t sw2 = gemm_tc_split_workspace_bytes(2, kG4, kLstmH, (int)rt);
             if (sw2 > sw) sw = sw2;
@@ -397,7 +404,9 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
     // inference workspaces carry no GEMM workspace: actor batches are small and run on the fp32 FFMA kernels
     const int mode = w->gemm_ws ? l->cfg.gemm_mode : FI_GEMM_SIMT;
     const int rt = m * t;
-    {
+    // the recurrence on the tensor cores (lstm_tc.cu) needs the BPTT state arrays of a training workspace
+    const bool lstm_tc = farmer_use_half(l, w, rt) && w->hp_hi && w->cst && lstm_tc_enabled();
+    if (!lstm_tc) {
         LaunchScope ls("transpose_whh_kernel", st, 2.0 * 4 * kG4 * kLstmH, kWorkBytes);
         transpose_whh_kernel<<<(kG4 * kLstmH + 255) / 256, 256, 0, st>>>(params + T[1].offset, w->whh_t);
         FI_TRY(ls.done());
@@ -410,13 +419,21 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         FI_TRY(launch_split_h(z, ldz, (size_t)rt, kZDim, kObsLdH, w->obs_hi, w->obs_lo, w->hs + kHsObs, 1, st));
         FI_TRY(launch_split_h(params + T[0].offset, kZDim, kG4, kZDim, kObsLdH, w->wih_hi, w->wih_lo, w->hs + kHsWih, 1, st));
         const SplitMat a{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, b{w->wih_hi, w->wih_lo, kObsLdH, w->hs + kHsWih};
-        FI_TRY(launch_gemm_tc_split(0, rt, kG4, kZDim, a, b, TcOut{w->gates, kG4, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
-                                    params + T[2].offset, 0, nullptr, 0, nullptr, 0, st));
+        TcOut out{w->gates, kG4, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
+        if (lstm_tc) {   // straight into the blocked layout the recurrent kernels move with one bulk copy per CTA and step
+            out.step_t = t;
+            out.step_nblk = (m + kStepBlockRows - 1) / kStepBlockRows;
+        }
+        FI_TRY(launch_gemm_tc_split(0, rt, kG4, kZDim, a, b, out, params + T[2].offset, 0, nullptr, 0, nullptr, 0, st));
     } else {
         FI_TRY(launch_gemm(mode, 0, rt, kG4, kZDim, z, ldz, params + T[0].offset, kZDim, w->gates, kG4, params + T[2].offset,
                            0, nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
     }
-    {
+    if (lstm_tc) {
+        // h_{s-1} leaves the kernel as the fp16 pairs the W_hh gradient product reads (scale 2^13: |h| <= 1)
+        FI_TRY(launch_lstm_forward_tc(w->gates, params + T[1].offset, params + T[3].offset, m, t, w->hp_hi, w->hp_lo, w->hs + kHsHp, w->cst,
+                                      w->feat, kFeat, st));
+    } else {
         // recurrent flops: 2 * 128 * 512 per (row, step)
         LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
         static std::atomic<uint64_t> fwd_attr{0};
@@ -479,7 +496,13 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         ldd = k;
     }
     // d = dfeat [m, 612]; BPTT turns the stored gates into pre-activation gate gradients
-    {
+    const int rt = m * t;
+    const bool lstm_tc = farmer_use_half(l, w, rt) && lstm_tc_enabled();
+    if (lstm_tc) {
+        // also leaves db_ih = db_hh (the column sums of dG) and max |dG|
+        FI_TRY(launch_lstm_backward_tc(w->gates, p->params + T[1].offset, w->cst, d, kFeat, m, t, w->hs + kHsDg, w->bias_part,
+                                       g + T[2].offset, g + T[3].offset, st));
+    } else {
         LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
         static std::atomic<uint64_t> bwd_attr{0};
         FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
@@ -487,13 +510,19 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
                                                                                       w->cst, d, kFeat, m, t);
         FI_TRY(ls.done());
     }
-    const int rt = m * t;
     if (farmer_use_half(l, w, rt)) {
-        // dW_ih = dgates^T z, dW_hh = dgates^T h_prev: the gate gradients are split once and read MN-major by both
-        FI_TRY(launch_amax(w->gates, kG4, (size_t)rt, kG4, w->hs + kHsDg, st));
-        FI_TRY(launch_amax(w->hprev, kLstmH, (size_t)rt, kLstmH, w->hs + kHsHp, st));
-        FI_TRY(launch_split_h(w->gates, kG4, (size_t)rt, kG4, kG4, w->dg_hi, w->dg_lo, w->hs + kHsDg, 1, st));
-        FI_TRY(launch_split_h(w->hprev, kLstmH, (size_t)rt, kLstmH, kLstmH, w->hp_hi, w->hp_lo, w->hs + kHsHp, 1, st));
+        // dW_ih = dgates^T z, dW_hh = dgates^T h_prev: the gate gradients are split once and read MN-major by both. The
+        // tensor-core recurrence has already left max |dG| and h_prev as fp16 pairs.
+        if (!lstm_tc) {
+            FI_TRY(launch_amax(w->gates, kG4, (size_t)rt, kG4, w->hs + kHsDg, st));
+            FI_TRY(launch_amax(w->hprev, kLstmH, (size_t)rt, kLstmH, w->hs + kHsHp, st));
+        }
+        if (lstm_tc) {
+            FI_TRY(launch_lstm_split_gates(w->gates, m, t, w->dg_hi, w->dg_lo, w->hs + kHsDg, st));
+        } else {
+            FI_TRY(launch_split_h(w->gates, kG4, (size_t)rt, kG4, kG4, w->dg_hi, w->dg_lo, w->hs + kHsDg, 1, st));
+            FI_TRY(launch_split_h(w->hprev, kLstmH, (size_t)rt, kLstmH, kLstmH, w->hp_hi, w->hp_lo, w->hs + kHsHp, 1, st));
+        }
         const SplitMat dg{w->dg_hi, w->dg_lo, kG4, w->hs + kHsDg};
         const SplitMat obs{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, hp{w->hp_hi, w->hp_lo, kLstmH, w->hs + kHsHp};
         FI_TRY(launch_gemm_tc_split(2, kG4, kZDim, rt, dg, obs, TcOut{g + T[0].offset, kZDim, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
@@ -506,8 +535,10 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         FI_TRY(launch_gemm(mode, 2, kG4, kLstmH, rt, w->gates, kG4, w->hprev, kLstmH, g + T[1].offset, kLstmH, nullptr, 0,
                            nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
     }
-    FI_TRY(launch_colsum(w->gates, kG4, rt, kG4, g + T[2].offset, w->colsum_ws, w->colsum_ws_bytes, st));
-    FI_TRY(launch_copy_words(g + T[3].offset, g + T[2].offset, kG4, st));   // d b_hh = d b_ih (a kernel: no copy engine on this stream)
+    if (!lstm_tc) {
+        FI_TRY(launch_colsum(w->gates, kG4, rt, kG4, g + T[2].offset, w->colsum_ws, w->colsum_ws_bytes, st));
+        FI_TRY(launch_copy_words(g + T[3].offset, g + T[2].offset, kG4, st));   // d b_hh = d b_ih (a kernel: no copy engine on this stream)
+    }
     return FI_OK;
 }
 

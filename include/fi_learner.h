@@ -61,6 +61,10 @@ FI_API int fi_prof_collect(fi_prof_entry* out, int max_entries);
  * launches log the pipeline events of their first 4 CTAs; this copies the last log out. Layout [cta 0..3][role 0..2][4096]
  * of (clock64 << 8 | tag), 0 = unused. Returns the number of 8-byte entries or a negative fi_status. No reference counterpart. */
 FI_API int fi_debug_tc_trace(void* host, size_t bytes);
+/* Diagnostics / tests: selects the implementation of the FarmerLstm recurrence (reference cmd/libtorch_bench/main.cpp:25-27):
+ * 1 = tcgen05 kernels over clusters of 8 CTAs (csrc/lstm_tc.cu; needs the 3xFP16 path), 0 = fp32 FFMA kernels
+ * (csrc/model_farmer.cu), -1 = as FI_LSTM_TC in the environment says (default 0). No reference counterpart. */
+FI_API void fi_debug_set_lstm_tc(int on);
 
 /* ============================ trajectory ring ============================================
  * Replaces SharedBuffer (include/freeimpala/data_structures.h:191-307). One ring per

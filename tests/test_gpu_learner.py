@@ -333,6 +333,44 @@ def test_farmer_step_vs_reference_golden(fi, oracle, ci, gemm_mode):
     L.close()
 
 
+@pytest.mark.parametrize("live", ["64", "128"])
+@pytest.mark.parametrize("ci", [3, 6, 7])
+def test_farmer_step_with_the_tensor_core_recurrence(fi, oracle, ci, live, monkeypatch):
+    """The opt-in tcgen05 recurrence (csrc/lstm_tc.cu: clusters of 8 CTAs, h exchanged with bulk copies into distributed
+    shared memory, gates and c kept in 64-row blocks) gives the same step as the reference: losses, gradients against the
+    reference's goldens and the float64 oracle, with 64 and with 128 batch rows per cluster (case 6, 9 x 33, has padding rows
+    in its only cluster; case 7, 1024 x 100, fills 16 / 8 clusters)."""
+    from freeimpala_b200 import _lib
+    g = np.load(os.path.join(U.GOLDEN, "farmer_step.npz"))
+    stride = int(g["stride"][0])
+    b, t, steps, ps, ys, bs = (int(v) for v in g[f"c{ci}_meta"])
+    loss, opt = (str(v) for v in g[f"c{ci}_kind"])
+    lr = float(g[f"c{ci}_lr"][0])
+    params = U.farmer_params(ps)
+    monkeypatch.setenv("FI_LSTM_LIVE", live)   # batch rows per cluster, read at every launch
+    _lib.load().fi_debug_set_lstm_tc(1)
+    try:
+        L = _farmer_learner(fi, b, t, loss=loss, optimizer=opt, lr=lr, gemm_mode="tcgen05_f16")
+        L.set_params(0, params)
+        O = oracle.farmer(params, opt=opt, lr=lr, loss=loss)
+        for s in range(steps):
+            z, x, tg = U.farmer_batch(bs + s, b, t)
+            L.forward_backward(0, L.stage_batch(0, po.pack_farmer_slots(z, x, tg)))
+            want_loss = float(g[f"c{ci}_losses"][s])
+            assert abs(L.last_losses(0)[0] - want_loss) <= TOL * abs(want_loss) + 1e-7
+            O.loss_grad(z, x, tg)
+            grads = L.get_grads(0)
+            assert U.rel_l2(grads[::stride], g[f"c{ci}_grads"][s]) < 2e-5
+            assert U.rel_l2(grads, O.grads()) < TOL
+            L.apply_update(0)
+            O.set_grads(np.asarray(grads, np.float64))   # teacher-forced, as in the test above
+            O.opt_step()
+        assert U.rel_l2(L.get_params(0)[::stride], g[f"c{ci}_params"]) < PARAM_TOL_VS_REFERENCE
+        L.close()
+    finally:
+        _lib.load().fi_debug_set_lstm_tc(-1)
+
+
 def test_farmer_step_through_ring_decodes_records(fi, oracle):
     """Batch assembly + record decode: trajectories written through the ring give the oracle's loss."""
     b, t = 6, 10
