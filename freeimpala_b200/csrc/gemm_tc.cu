@@ -808,6 +808,12 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int ld_in, size_t
     }
 }
 
+// FI_COOP=0: the fused max|x| + split pre-passes (one cooperative launch each) as separate launches (A/B measurements)
+static bool coop_prepass() {
+    static const bool on = [] { const char* e = getenv("FI_COOP"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int launch_split_tf32(const float* x, int ld_in, size_t rows, int cols, int ld_out, float* hi, float* lo, cudaStream_t st) {
     if (rows == 0 || ld_out == 0) return FI_OK;
     const size_t total = rows * (size_t)ld_out;
@@ -936,6 +942,10 @@ amax_split_h_kernel(const float* __restrict__ x, int ld_in, size_t rows, int col
 }
 
 int launch_amax_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out, void* hi, void* lo, HScale* hs, cudaStream_t st) {
+    if (!coop_prepass()) {   // FI_COOP=0: two ordinary launches
+        FI_TRY(launch_amax(x, ld_in, rows, cols, hs, st));
+        return launch_split_h(x, ld_in, rows, cols, ld_out, hi, lo, hs, 1, st);
+    }
     if (rows == 0 || ld_out == 0) return FI_OK;
     if (ld_out & 1) return set_error(FI_ERR_ARG, "split_h: ld_out must be even");
     // every block must be resident for the grid barrier: as many blocks as fit (queried once per device), capped by the work
@@ -1008,6 +1018,11 @@ amax_split_params_kernel(const float* __restrict__ p, int n, int ld_flat, __half
 
 int launch_amax_split_params(const float* p, int n, int ld_flat, void* hi, void* lo, const float* w, int w_rows, int w_cols, int ld2,
                              void* hi2, void* lo2, HScale* hs, cudaStream_t st) {
+    if (!coop_prepass()) {   // FI_COOP=0: three ordinary launches
+        FI_TRY(launch_amax(p, n, 1, n, hs, st));
+        FI_TRY(launch_split_h(p, n, 1, n, ld_flat, hi, lo, hs, 1, st));
+        return launch_split_h(w, w_cols, w_rows, w_cols, ld2, hi2, lo2, hs, 0, st);
+    }
     if ((ld_flat & 1) || (ld2 & 1)) return set_error(FI_ERR_ARG, "split_h: row strides must be even");
     __half2 *a = static_cast<__half2*>(hi), *b = static_cast<__half2*>(lo), *c = static_cast<__half2*>(hi2), *d = static_cast<__half2*>(lo2);
     void* args[] = {(void*)&p, (void*)&n, (void*)&ld_flat, (void*)&a, (void*)&b, (void*)&w, (void*)&w_rows, (void*)&w_cols, (void*)&ld2,

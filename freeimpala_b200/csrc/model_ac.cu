@@ -46,11 +46,6 @@ struct AcTc {  // tensor-core path state, owned by the Player (Player::ac_tc)
     size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
-// FI_COOP=0: the amax and split pre-passes as separate launches instead of one cooperative launch each (A/B measurements)
-static bool coop_prepass() {
-    static const bool on = [] { const char* e = getenv("FI_COOP"); return !(e && e[0] == '0'); }();
-    return on;
-}
 static bool use_tc(const fi_learner* l) { return l->cfg.gemm_mode != FI_GEMM_SIMT && gemm_tc_available(); }
 
 int ac_alloc(fi_learner* l, Player* p) {
@@ -228,20 +223,12 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
         // one scale for the whole parameter arena (weights and biases), one for the observations; every activation and
         // back-propagated gradient gets its scale from the producing GEMM (bound k * amax_a * amax_b, gemm_tc.cu)
         FI_TRY(launch_zero2(hs, kHsCount * sizeof(HScale), p->d_losses, 4 * sizeof(double), st));
+        // parameters: max |p|, the split of the arena and dense1.w's re-laid-out copy in one cooperative launch
         const int arena_ld = (int)((l->arena_elems + 7) & ~(size_t)7);
-        if (coop_prepass()) {
-            // parameters: max |p|, the split of the arena and dense1.w's re-laid-out copy in one cooperative launch
-            FI_TRY(launch_amax_split_params(p->params, (int)l->arena_elems, arena_ld, tc->w_hi, tc->w_lo, p->params + T[0].offset, kHid, kZDim,
-                                            tc->obs_ld, tc->w1_hi, tc->w1_lo, hs + kHsW, st));
-            // observations: max |x| and the split in one cooperative launch (the second pass reads the batch out of L2)
-            FI_TRY(launch_amax_split_h(batch, kRecWords, (size_t)rows, kZDim, tc->obs_ld, tc->obs_hi, tc->obs_lo, hs + kHsObs, st));
-        } else {
-            FI_TRY(launch_amax(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, hs + kHsW, st));
-            FI_TRY(launch_amax(batch, kRecWords, (size_t)rows, kZDim, hs + kHsObs, st));
-            FI_TRY(launch_split_h(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, arena_ld, tc->w_hi, tc->w_lo, hs + kHsW, 1, st));
-            FI_TRY(launch_split_h(p->params + T[0].offset, kZDim, kHid, kZDim, tc->obs_ld, tc->w1_hi, tc->w1_lo, hs + kHsW, 0, st));
-            FI_TRY(launch_split_h(batch, kRecWords, (size_t)rows, kZDim, tc->obs_ld, tc->obs_hi, tc->obs_lo, hs + kHsObs, 1, st));
-        }
+        FI_TRY(launch_amax_split_params(p->params, (int)l->arena_elems, arena_ld, tc->w_hi, tc->w_lo, p->params + T[0].offset, kHid, kZDim,
+                                        tc->obs_ld, tc->w1_hi, tc->w1_lo, hs + kHsW, st));
+        // observations: max |x| and the split in one cooperative launch (the second pass reads the batch out of L2)
+        FI_TRY(launch_amax_split_h(batch, kRecWords, (size_t)rows, kZDim, tc->obs_ld, tc->obs_hi, tc->obs_lo, hs + kHsObs, st));
     } else {
         FI_TRY(launch_split_tf32(p->params, (int)l->arena_elems, 1, (int)l->arena_elems, (int)l->arena_elems, (float*)tc->w_hi, (float*)tc->w_lo, st));
         FI_TRY(launch_split_tf32(p->params + T[0].offset, kZDim, kHid, kZDim, kObsLd, (float*)tc->w1_hi, (float*)tc->w1_lo, st));
@@ -265,12 +252,7 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     if (H) {  // the loss head writes plain fp32 rows; max |x| and the fp16 split follow (13 MB)
         FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                        c.baseline_cost, c.entropy_cost, tc->dhead, nullptr, nullptr, p->d_losses, st));
-        if (coop_prepass()) {
-            FI_TRY(launch_amax_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, st));
-        } else {
-            FI_TRY(launch_amax(tc->dhead, kHead, (size_t)rows, kHead, hs + kHsDhead, st));
-            FI_TRY(launch_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, 1, st));
-        }
+        FI_TRY(launch_amax_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, st));
     } else {
         FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                        c.baseline_cost, c.entropy_cost, nullptr, nullptr, nullptr, p->d_losses, st, (float*)tc->dhead_hi,

@@ -44,7 +44,28 @@ struct FarmerWs {
     void *hp_hi = nullptr, *hp_lo = nullptr;       // [rows*T, 128]
     void* split_ws = nullptr; size_t split_ws_bytes = 0;
     float* bias_part = nullptr;                    // [ceil(rows / 64), 512]: per-cluster bias-gradient partials of the tensor-core BPTT
+    // Dense stack on the tensor cores, as model_ac.cu runs its trunk: the parameter arena split once per step, every
+    // activation and back-propagated gradient written as fp16 pairs by the GEMM that produces it (with its ReLU bit mask /
+    // the per-32-row column sums for the bias gradient), split-K slabs and column sums reduced by two launches at the end.
+    HScale* dhs = nullptr;                         // [kDhCount]
+    void *w_hi = nullptr, *w_lo = nullptr;         // split parameter arena (same element offsets as params)
+    void *w1_hi = nullptr, *w1_lo = nullptr;       // dense1.w re-laid out as [512, 640]
+    void *feat_hi = nullptr, *feat_lo = nullptr;   // [rows, 640]
+    void* act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t* relu_bits[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* dd_hi[2] = {nullptr, nullptr};
+    void* dd_lo[2] = {nullptr, nullptr};
+    void *dy_hi = nullptr, *dy_lo = nullptr;       // [rows, 32], columns 1..31 stay zero
+    float* dfeat = nullptr;                        // [rows, 128]: dL/dh_{T-1} (the x part of the feature row needs no gradient)
+    float* colsum_part[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* colsum_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* slab_ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t slab_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
+constexpr int kFeatLdH = 640;   // 612 feature columns padded to whole 128-byte lines of fp16
+constexpr int kDyLd = 32;
+enum { kDhW = 0, kDhFeat = 1, kDhDy = 2, kDhAct0 = 3, kDhD0 = 8, kDhCount = 14 };
 constexpr int kObsLdH = 192;   // 162 observation words padded to three whole 128-byte lines of fp16 (see model_ac.cu)
 enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
 
@@ -306,9 +327,17 @@ static void ws_release(FarmerWs* w) {
         if (p) cudaFree(p);
     if (w->gemm_ws) cudaFree(w->gemm_ws);
     if (w->colsum_ws) cudaFree(w->colsum_ws);
-    void* h[] = {w->hs, w->obs_hi, w->obs_lo, w->wih_hi, w->wih_lo, w->dg_hi, w->dg_lo, w->hp_hi, w->hp_lo, w->split_ws, w->bias_part};
+    void* h[] = {w->hs, w->obs_hi, w->obs_lo, w->wih_hi, w->wih_lo, w->dg_hi, w->dg_lo, w->hp_hi, w->hp_lo, w->split_ws, w->bias_part,
+                 w->dhs, w->w_hi, w->w_lo, w->w1_hi, w->w1_lo, w->feat_hi, w->feat_lo, w->dd_hi[0], w->dd_hi[1], w->dd_lo[0], w->dd_lo[1],
+                 w->dy_hi, w->dy_lo, w->dfeat};
     for (void* p : h)
         if (p) cudaFree(p);
+    for (int i = 0; i < 6; i++) {
+        void* q[] = {i < 5 ? w->act_hi[i] : nullptr, i < 5 ? w->act_lo[i] : nullptr, i < 5 ? (void*)w->relu_bits[i] : nullptr,
+                     i < 5 ? (void*)w->colsum_part[i] : nullptr, w->colsum_scratch[i], w->slab_ws[i]};
+        for (void* p : q)
+            if (p) cudaFree(p);
+    }
     delete w;
 }
 
@@ -372,6 +401,35 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
             if (sw2 > sw) sw = sw2;
             w->split_ws_bytes = sw;
             if (sw) FI_CUDA_OK(cudaMalloc(&w->split_ws, sw));
+            // dense stack
+            const size_t ab = ((l->arena_elems + 7) & ~(size_t)7) * 2, rb = rows * kHid * 2;
+            FI_CUDA_OK(cudaMalloc((void**)&w->dhs, kDhCount * sizeof(HScale)));
+            FI_CUDA_OK(cudaMalloc(&w->w_hi, ab));
+            FI_CUDA_OK(cudaMalloc(&w->w_lo, ab));
+            FI_CUDA_OK(cudaMalloc(&w->w1_hi, (size_t)kHid * kFeatLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->w1_lo, (size_t)kHid * kFeatLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->feat_hi, rows * kFeatLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->feat_lo, rows * kFeatLdH * 2));
+            FI_CUDA_OK(cudaMalloc(&w->dy_hi, rows * kDyLd * 2));
+            FI_CUDA_OK(cudaMalloc(&w->dy_lo, rows * kDyLd * 2));
+            FI_CUDA_OK(cudaMalloc((void**)&w->dfeat, rows * kLstmH * sizeof(float)));
+            const int part_rows = 4 * (int)((rows + 127) / 128);
+            for (int i = 0; i < 5; i++) {
+                FI_CUDA_OK(cudaMalloc(&w->act_hi[i], rb));
+                FI_CUDA_OK(cudaMalloc(&w->act_lo[i], rb));
+                FI_CUDA_OK(cudaMalloc((void**)&w->relu_bits[i], rows * (kHid / 32) * sizeof(uint32_t)));
+                FI_CUDA_OK(cudaMalloc((void**)&w->colsum_part[i], (size_t)part_rows * kHid * sizeof(float)));
+                FI_CUDA_OK(cudaMalloc((void**)&w->colsum_scratch[i], grad_colsum_scratch_bytes(part_rows, kHid)));
+                w->slab_bytes[i] = gemm_tc_split_workspace_bytes(2, kHid, i == 0 ? kFeat : kHid, (int)rows);
+            }
+            for (int i = 0; i < 2; i++) {
+                FI_CUDA_OK(cudaMalloc(&w->dd_hi[i], rb));
+                FI_CUDA_OK(cudaMalloc(&w->dd_lo[i], rb));
+            }
+            FI_CUDA_OK(cudaMalloc((void**)&w->colsum_scratch[5], grad_colsum_scratch_bytes((int)rows, 1)));
+            w->slab_bytes[5] = gemm_tc_split_workspace_bytes(2, kHid, 1, (int)rows);
+            for (int i = 0; i < 6; i++)
+                if (w->slab_bytes[i]) FI_CUDA_OK(cudaMalloc(&w->slab_ws[i], w->slab_bytes[i]));
         }
     }
     return FI_OK;
@@ -397,6 +455,12 @@ static bool farmer_use_half(const fi_learner* l, const FarmerWs* w, int rt) {
     return w->half && (l->cfg.gemm_mode == FI_GEMM_TCGEN05_F16 || 2.0 * rt * kG4 * kZDim >= 64e6);
 }
 
+// The dense stack runs on the tensor cores (3xFP16, fused epilogues) when that format is required, and under AUTO from 128
+// batch rows up (below that the fp32 FFMA kernels win: every product is launch-latency bound).
+static bool farmer_dense_tc(const fi_learner* l, const FarmerWs* w, int m) {
+    return w->half && w->dhs && (l->cfg.gemm_mode == FI_GEMM_TCGEN05_F16 || m >= 128);
+}
+
 // z rows: (b,t) at z + (b*t + s) * ldz. Leaves y[m], feat, act (and the BPTT state when training).
 static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const float* z, int ldz, int m, int t,
                           cudaStream_t st) {
@@ -411,14 +475,21 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         transpose_whh_kernel<<<(kG4 * kLstmH + 255) / 256, 256, 0, st>>>(params + T[1].offset, w->whh_t);
         FI_TRY(ls.done());
     }
+    const bool half_proj = farmer_use_half(l, w, rt), dense_tc = farmer_dense_tc(l, w, m);
+    if (half_proj || dense_tc) FI_TRY(launch_zero2(w->hs, 4 * sizeof(HScale), w->dhs, w->dhs ? kDhCount * sizeof(HScale) : 0, st));
+    if (dense_tc) {
+        // parameters: max |p|, the split of the whole arena and dense1.w's copy with padded rows, one launch
+        const int arena_ld = (int)((l->arena_elems + 7) & ~(size_t)7);
+        FI_TRY(launch_amax_split_params(params, (int)l->arena_elems, arena_ld, w->w_hi, w->w_lo, params + T[4].offset, kHid, kFeat, kFeatLdH,
+                                        w->w1_hi, w->w1_lo, w->dhs + kDhW, st));
+    }
     // gates = z W_ih^T + b_ih for all B*T rows at once
-    if (farmer_use_half(l, w, rt)) {
-        FI_TRY(launch_zero2(w->hs, 4 * sizeof(HScale), nullptr, 0, st));
-        FI_TRY(launch_amax(z, ldz, (size_t)rt, kZDim, w->hs + kHsObs, st));
-        FI_TRY(launch_amax(params + T[0].offset, kZDim, kG4, kZDim, w->hs + kHsWih, st));
-        FI_TRY(launch_split_h(z, ldz, (size_t)rt, kZDim, kObsLdH, w->obs_hi, w->obs_lo, w->hs + kHsObs, 1, st));
-        FI_TRY(launch_split_h(params + T[0].offset, kZDim, kG4, kZDim, kObsLdH, w->wih_hi, w->wih_lo, w->hs + kHsWih, 1, st));
-        const SplitMat a{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, b{w->wih_hi, w->wih_lo, kObsLdH, w->hs + kHsWih};
+    if (half_proj) {
+        FI_TRY(launch_amax_split_h(z, ldz, (size_t)rt, kZDim, kObsLdH, w->obs_hi, w->obs_lo, w->hs + kHsObs, st));
+        HScale* wih_hs = dense_tc ? w->dhs + kDhW : w->hs + kHsWih;   // the arena's scale bounds W_ih as well
+        if (!dense_tc) FI_TRY(launch_amax(params + T[0].offset, kZDim, kG4, kZDim, wih_hs, st));
+        FI_TRY(launch_split_h(params + T[0].offset, kZDim, kG4, kZDim, kObsLdH, w->wih_hi, w->wih_lo, wih_hs, dense_tc ? 0 : 1, st));
+        const SplitMat a{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, b{w->wih_hi, w->wih_lo, kObsLdH, wih_hs};
         TcOut out{w->gates, kG4, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
         if (lstm_tc) {   // straight into the blocked layout the recurrent kernels move with one bulk copy per CTA and step
             out.step_t = t;
@@ -441,6 +512,26 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
             w->gates, w->whh_t, params + T[3].offset, m, t, w->hprev, w->cst, w->feat);
         FI_TRY(ls.done());
+    }
+    if (dense_tc) {
+        // x_l = relu(x_{l-1} W_l^T + b_l), written as fp16 pairs (and ReLU bit masks) by the GEMM epilogue; y = x_5 w_6 + b_6
+        HScale* dhs = w->dhs;
+        FI_TRY(launch_amax_split_h(w->feat, kFeat, (size_t)m, kFeat, kFeatLdH, w->feat_hi, w->feat_lo, dhs + kDhFeat, st));
+        auto W = [&](int tensor, int ld) {
+            return SplitMat{static_cast<char*>(w->w_hi) + T[tensor].offset * 2, static_cast<char*>(w->w_lo) + T[tensor].offset * 2, ld, dhs + kDhW};
+        };
+        for (int layer = 0; layer < 5; layer++) {
+            const SplitMat x = layer == 0 ? SplitMat{w->feat_hi, w->feat_lo, kFeatLdH, dhs + kDhFeat}
+                                          : SplitMat{w->act_hi[layer - 1], w->act_lo[layer - 1], kHid, dhs + kDhAct0 + layer - 1};
+            const SplitMat wm = layer == 0 ? SplitMat{w->w1_hi, w->w1_lo, kFeatLdH, dhs + kDhW} : W(4 + 2 * layer, kHid);
+            const TcOut out{nullptr, 0, w->act_hi[layer], w->act_lo[layer], kHid, 0, nullptr, w->relu_bits[layer], kHid / 32, nullptr,
+                            dhs + kDhAct0 + layer, dhs + kDhW};
+            FI_TRY(launch_gemm_tc_split(0, m, kHid, layer == 0 ? kFeat : kHid, x, wm, out, params + T[5 + 2 * layer].offset, 1, nullptr, 0,
+                                        nullptr, 0, st));
+        }
+        return launch_gemm_tc_split(0, m, 1, kHid, SplitMat{w->act_hi[4], w->act_lo[4], kHid, dhs + kDhAct0 + 4}, W(14, kHid),
+                                    TcOut{w->y, 1, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr}, params + T[15].offset, 0, nullptr, 0,
+                                    nullptr, 0, st);
     }
     const float* x = w->feat;
     int k = kFeat;
@@ -474,15 +565,71 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
                                                               w->dy, p->d_losses);
         FI_TRY(ls.done());
     }
+    float* d = w->d_a;
+    int ldd = kHid;
+    const bool dense_tc = farmer_dense_tc(l, w, m);
+    if (dense_tc) {
+        // As model_ac.cu's backward: every dgrad epilogue applies the ReLU bit mask, writes the next gradient as fp16 pairs and
+        // leaves per-32-row column sums (the bias gradient); wgrad split-K slabs and those sums are reduced by two launches.
+        HScale* dhs = w->dhs;
+        auto W = [&](int tensor, int ld) {
+            return SplitMat{static_cast<char*>(w->w_hi) + T[tensor].offset * 2, static_cast<char*>(w->w_lo) + T[tensor].offset * 2, ld, dhs + kDhW};
+        };
+        auto ACT = [&](int layer) { return SplitMat{w->act_hi[layer], w->act_lo[layer], kHid, dhs + kDhAct0 + layer}; };
+        FI_TRY(launch_amax_split_h(w->dy, 1, (size_t)m, 1, kDyLd, w->dy_hi, w->dy_lo, dhs + kDhDy, st));
+        const SplitMat dy{w->dy_hi, w->dy_lo, kDyLd, dhs + kDhDy};
+        GradSegTable segs;
+        int splits = 1;
+        const int part_rows = 4 * ((m + 127) / 128);
+        FI_TRY(grad_table_add_colsum(&segs, w->dy, 1, m, 1, g + T[15].offset, w->colsum_scratch[5]));
+        {
+            TcOut o{g + T[14].offset, kHid, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, nullptr};
+            o.deferred_splits = &splits;
+            FI_TRY(launch_gemm_tc_split(2, kHid, 1, m, ACT(4), dy, o, nullptr, 0, nullptr, 0, w->slab_ws[5], w->slab_bytes[5], st));
+            if (splits > 1) FI_TRY(grad_table_add_slabs(&segs, (const float*)w->slab_ws[5], splits, (size_t)kHid, kHid, g + T[14].offset));
+        }
+        int cur = 0, dslot = kDhD0;
+        FI_TRY(launch_gemm_tc_split(1, m, kHid, 1, dy, W(14, kHid),
+                                    TcOut{nullptr, 0, w->dd_hi[cur], w->dd_lo[cur], kHid, 0, w->relu_bits[4], nullptr, kHid / 32,
+                                          w->colsum_part[4], dhs + dslot, nullptr},
+                                    nullptr, 0, nullptr, 0, nullptr, 0, st));
+        for (int layer = 4; layer >= 0; layer--) {
+            const SplitMat dl{w->dd_hi[cur], w->dd_lo[cur], kHid, dhs + dslot};
+            const SplitMat x = layer == 0 ? SplitMat{w->feat_hi, w->feat_lo, kFeatLdH, dhs + kDhFeat} : ACT(layer - 1);
+            const int k = layer == 0 ? kFeat : kHid;
+            FI_TRY(grad_table_add_colsum(&segs, w->colsum_part[layer], kHid, part_rows, kHid, g + T[5 + 2 * layer].offset, w->colsum_scratch[layer]));
+            {
+                TcOut o{g + T[4 + 2 * layer].offset, k, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
+                o.deferred_splits = &splits;
+                FI_TRY(launch_gemm_tc_split(2, kHid, k, m, dl, x, o, nullptr, 0, nullptr, 0, w->slab_ws[layer], w->slab_bytes[layer], st));
+                if (splits > 1)
+                    FI_TRY(grad_table_add_slabs(&segs, (const float*)w->slab_ws[layer], splits, (size_t)kHid * k, kHid * k, g + T[4 + 2 * layer].offset));
+            }
+            if (layer > 0) {
+                FI_TRY(launch_gemm_tc_split(1, m, kHid, kHid, dl, W(4 + 2 * layer, kHid),
+                                            TcOut{nullptr, 0, w->dd_hi[cur ^ 1], w->dd_lo[cur ^ 1], kHid, 0, w->relu_bits[layer - 1], nullptr,
+                                                  kHid / 32, w->colsum_part[layer - 1], dhs + dslot + 1, nullptr},
+                                            nullptr, 0, nullptr, 0, nullptr, 0, st));
+                cur ^= 1;
+                dslot++;
+            } else {
+                // dL/dh_{T-1} = the first 128 columns of d0 W_1 (the x part of the feature row takes no gradient)
+                FI_TRY(launch_gemm_tc_split(1, m, kLstmH, kHid, dl, SplitMat{w->w1_hi, w->w1_lo, kFeatLdH, dhs + kDhW},
+                                            TcOut{w->dfeat, kLstmH, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr}, nullptr, 0, nullptr,
+                                            0, nullptr, 0, st));
+            }
+        }
+        FI_TRY(launch_grad_finalize(&segs, st));
+        d = w->dfeat;
+        ldd = kLstmH;
+    } else {
     // dense6: dW = dy^T act4, db = sum dy, d4 = (dy W6) * relu'(act4)
     FI_TRY(launch_colsum(w->dy, 1, m, 1, g + T[15].offset, w->colsum_ws, w->colsum_ws_bytes, st));
     FI_TRY(launch_gemm(mode, 2, 1, kHid, m, w->dy, 1, w->act[4], kHid, g + T[14].offset, kHid, nullptr, 0, nullptr, 0,
                        w->gemm_ws, w->gemm_ws_bytes, st));
-    float* d = w->d_a;
     float* d_next = w->d_b;
     FI_TRY(launch_gemm(mode, 1, m, kHid, 1, w->dy, 1, p->params + T[14].offset, kHid, d, kHid, nullptr, 0, w->act[4], kHid,
                        w->gemm_ws, w->gemm_ws_bytes, st));
-    int ldd = kHid;
     for (int layer = 4; layer >= 0; layer--) {
         const float* in = layer == 0 ? w->feat : w->act[layer - 1];
         const int k = layer == 0 ? kFeat : kHid;
@@ -495,19 +642,20 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         float* tmp = d; d = d_next; d_next = tmp;
         ldd = k;
     }
-    // d = dfeat [m, 612]; BPTT turns the stored gates into pre-activation gate gradients
+    }   // !dense_tc
+    // d = dfeat [m, ldd]: its first 128 columns are dL/dh_{T-1}; BPTT turns the stored gates into pre-activation gate gradients
     const int rt = m * t;
     const bool lstm_tc = farmer_use_half(l, w, rt) && lstm_tc_enabled();
     if (lstm_tc) {
         // also leaves db_ih = db_hh (the column sums of dG) and max |dG|
-        FI_TRY(launch_lstm_backward_tc(w->gates, p->params + T[1].offset, w->cst, d, kFeat, m, t, w->hs + kHsDg, w->bias_part,
+        FI_TRY(launch_lstm_backward_tc(w->gates, p->params + T[1].offset, w->cst, d, ldd, m, t, w->hs + kHsDg, w->bias_part,
                                        g + T[2].offset, g + T[3].offset, st));
     } else {
         LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
         static std::atomic<uint64_t> bwd_attr{0};
         FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
         lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset,
-                                                                                      w->cst, d, kFeat, m, t);
+                                                                                      w->cst, d, ldd, m, t);
         FI_TRY(ls.done());
     }
     if (farmer_use_half(l, w, rt)) {
@@ -545,6 +693,7 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
 int farmer_activation(Player* p, int layer, const float** a, const float** lo) {
     FarmerWs* w = static_cast<FarmerWs*>(p->farmer_ws);
     if (!w || layer < 0 || layer >= 5) return set_error(FI_ERR_ARG, "no such hidden layer %d", layer);
+    if (w->dhs) return set_error(FI_ERR_STATE, "the dense stack may have run on fp16 pairs: no fp32 activations to read back");
     *a = w->act[layer];
     *lo = nullptr;
     return FI_OK;
