@@ -140,6 +140,8 @@ int launch_lstm_forward_tc(float* gates, const float* whh, const float* b_hh, in
 // gates / cst: blocked arrays (step_block_offset below), rows padded to 64. bias_part: [ceil(m / 64), 512] scratch.
 int launch_lstm_backward_tc(float* gates, const float* whh, const float* cst, const float* dfeat, int ldf, int m, int t, HScale* dg_hs,
                             float* bias_part, float* g_bih, float* g_bhh, cudaStream_t st);
+// db_ih = db_hh = sum over the BPTT kernel's CTAs (or clusters) of their column sums of dG, in index order
+int launch_lstm_bias_grad(const float* part, int nparts, float* g_bih, float* g_bhh, cudaStream_t st);
 int launch_lstm_split_gates(const float* gates, int m, int t, void* hi, void* lo, HScale* hs, cudaStream_t st);
 int launch_amax_split_params(const float* p, int n, int ld_flat, void* hi, void* lo, const float* w, int w_rows, int w_cols, int ld2,
                              void* hi2, void* lo2, HScale* hs, cudaStream_t st);

@@ -801,6 +801,12 @@ lstm_split_gates_kernel(const float* __restrict__ gates, int m, int t, int nblk,
     }
 }
 
+int launch_lstm_bias_grad(const float* part, int nparts, float* g_bih, float* g_bhh, cudaStream_t st) {
+    LaunchScope ls("lstm_bias_grad_kernel", st, 4.0 * kG4 * (nparts + 2), kWorkBytes);
+    lstm_bias_grad_kernel<<<2, 256, 0, st>>>(part, nparts, g_bih, g_bhh);
+    return ls.done();
+}
+
 int launch_lstm_split_gates(const float* gates, int m, int t, void* hi, void* lo, HScale* hs, cudaStream_t st) {
     LaunchScope ls("lstm_split_gates_kernel", st, 8.0 * m * t * kG4, kWorkBytes);
     lstm_split_gates_kernel<<<kNumSMs * 8, 256, 0, st>>>(gates, m, t, (m + kStepBlockRows - 1) / kStepBlockRows, static_cast<__half2*>(hi),
@@ -818,9 +824,7 @@ int launch_lstm_backward_tc(float* gates, const float* whh, const float* cst, co
                                                                                t, dg_hs, bias_part, lstm_trace_buffer());
     FI_TRY(ls.done());
     lstm_trace_report("backward", lstm_trace_buffer(), t, st);
-    LaunchScope lb("lstm_bias_grad_kernel", st, 4.0 * kG4 * (clusters + 2), kWorkBytes);
-    lstm_bias_grad_kernel<<<2, 256, 0, st>>>(bias_part, clusters, g_bih, g_bhh);
-    return lb.done();
+    return launch_lstm_bias_grad(bias_part, clusters, g_bih, g_bhh, st);
 }
 
 }  // namespace fi

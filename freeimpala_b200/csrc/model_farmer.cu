@@ -10,6 +10,8 @@
 // kernel that owns R batch rows per CTA for all T steps (rows are independent, so no inter-CTA
 // synchronisation); BPTT mirrors it and leaves the pre-activation gate gradients in place of
 // the gates, so dW_ih, dW_hh and the bias gradients are again single GEMMs / column sums.
+#include <cuda_fp16.h>
+
 #include "learner.cuh"
 
 namespace fi {
@@ -43,7 +45,7 @@ struct FarmerWs {
     void *dg_hi = nullptr, *dg_lo = nullptr;       // [rows*T, 512]
     void *hp_hi = nullptr, *hp_lo = nullptr;       // [rows*T, 128]
     void* split_ws = nullptr; size_t split_ws_bytes = 0;
-    float* bias_part = nullptr;                    // [ceil(rows / 64), 512]: per-cluster bias-gradient partials of the tensor-core BPTT
+    float* bias_part = nullptr;                    // [CTAs of the BPTT kernel, 512]: their column sums of dG (the LSTM bias gradient)
     // Dense stack on the tensor cores, as model_ac.cu runs its trunk: the parameter arena split once per step, every
     // activation and back-propagated gradient written as fp16 pairs by the GEMM that produces it (with its ReLU bit mask /
     // the per-32-row column sums for the bias gradient), split-K slabs and column sums reduced by two launches at the end.
@@ -117,11 +119,13 @@ __global__ void farmer_assemble_dense_kernel(const float* __restrict__ x, int m,
 // loaded before the product and added after it, so its global-memory latency hides behind the FMAs. (The first version gave one column to each of 512 threads and re-read h with 1024
 // scalar broadcast loads per thread and step: shared-memory-issue bound at 10 us per step.)
 constexpr int kLstmSmemK = 64;  // k-rows of W_hh^T kept in shared memory
+constexpr float kHprevScale = 8192.f;   // hscale_from_bound(1)
 constexpr size_t kLstmFwdSmem = ((size_t)kLstmSmemK * kG4 + kLstmRows * kG4 + kLstmH * kLstmRows + kLstmRows * kLstmH) * sizeof(float);
 
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, const float* __restrict__ b_hh,
-                    int m, int t, float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ feat) {
+                    int m, int t, float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ feat,
+                    __half* __restrict__ hp_hi, __half* __restrict__ hp_lo, HScale* __restrict__ hp_hs) {
     extern __shared__ __align__(16) float lstm_smem[];
     float* Ws = lstm_smem;                          // [64][512]   W_hh^T rows k < 64
     float* ps = Ws + kLstmSmemK * kG4;              // [8][512]    pre-activations of this step
@@ -135,6 +139,12 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(whh_t) + i);
     for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) { hs[i] = 0.f; cs[i] = 0.f; }
     const float2 bias = __ldg(reinterpret_cast<const float2*>(b_hh + j0));
+    if (hp_hs && blockIdx.x == 0 && tid == 0) {   // |h| <= 1: the fp16 pairs of h_prev use the constant scale 2^13, no max|x| pass
+        hp_hs->scale = kHprevScale;
+        hp_hs->inv = 1.f / kHprevScale;
+        hp_hs->amax = 1.f;
+        hp_hs->bound = 1.f;
+    }
     float2 wreg[kLstmH - kLstmSmemK];
 #pragma unroll
     for (int k = 0; k < kLstmH - kLstmSmemK; k++)
@@ -188,6 +198,12 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
                 g[u] = ig; g[kLstmH + u] = fg; g[2 * kLstmH + u] = gg; g[3 * kLstmH + u] = og;
                 if (cst) cst[row * kLstmH + u] = c;
                 if (hprev) hprev[row * kLstmH + u] = hs[u * kLstmRows + r];   // h_{s-1}
+                if (hp_hi) {   // ... or directly as the fp16 pair the W_hh gradient product reads
+                    const float hv = hs[u * kLstmRows + r] * kHprevScale;
+                    const __half hh = __float2half_rn(hv);
+                    hp_hi[row * kLstmH + u] = hh;
+                    hp_lo[row * kLstmH + u] = __float2half_rn((hv - __half2float(hh)) * 2048.f);
+                }
                 cs[r * kLstmH + u] = c;
                 if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = h;
             }
@@ -212,7 +228,7 @@ constexpr size_t kLstmBwdSmem = ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows +
 
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
-                     const float* __restrict__ dfeat, int ldf, int m, int t) {
+                     const float* __restrict__ dfeat, int ldf, int m, int t, HScale* __restrict__ dg_hs, float* __restrict__ bias_part) {
     extern __shared__ __align__(16) float lstm_smem[];
     float* Wh = lstm_smem;                          // [4][64][128] W_hh rows 128q + jj, jj < 64
     float* dgs = Wh + kLstmSmemJ * kLstmH;          // [512][8]    dG of this step, j-major
@@ -237,6 +253,9 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
 #pragma unroll
     for (int jj = 0; jj < 64; jj++) wreg[jj] = __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + 64 + jj) * kLstmH + k0));
     __syncthreads();
+    // max |dG| (for the fp16 split that follows) and this CTA's column sums of dG (the bias gradient): thread tid always
+    // meets unit tid % 128, rows tid / 128 + 2 k
+    float run_max = 0.f, bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
     for (int s = t - 1; s >= 0; s--) {
         for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
             const int r = i / kLstmH, u = i % kLstmH;
@@ -255,6 +274,8 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
                 d3 = dhv * tc * og * (1.f - og);
                 g[u] = d0; g[kLstmH + u] = d1; g[2 * kLstmH + u] = d2; g[3 * kLstmH + u] = d3;
                 dc[i] = dct * fg;
+                run_max = fmaxf(fmaxf(run_max, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
+                bs0 += d0; bs1 += d1; bs2 += d2; bs3 += d3;
             }
             dgs[u * kLstmRows + r] = d0;
             dgs[(kLstmH + u) * kLstmRows + r] = d1;
@@ -290,6 +311,19 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
                 dh[i] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
             __syncthreads();
         }
+    }
+    if (dg_hs) {
+        const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(run_max));
+        if ((tid & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&dg_hs->amax), wm);
+    }
+    if (bias_part) {   // fixed order: the two threads of a unit, then (lstm_bias_grad_kernel) the CTAs in index order
+        __syncthreads();
+        float* bq = part;   // [2][4][128]
+        const int half = tid >> 7, u = tid & 127;
+        bq[(half * 4 + 0) * kLstmH + u] = bs0; bq[(half * 4 + 1) * kLstmH + u] = bs1;
+        bq[(half * 4 + 2) * kLstmH + u] = bs2; bq[(half * 4 + 3) * kLstmH + u] = bs3;
+        __syncthreads();
+        for (int j = tid; j < kG4; j += kLstmThreads) bias_part[(size_t)blockIdx.x * kG4 + j] = bq[j] + bq[kG4 + j];
     }
 }
 
@@ -361,6 +395,7 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
         FI_CUDA_OK(cudaMalloc((void**)&w->cst, rt_pad * kLstmH * sizeof(float)));
         FI_CUDA_OK(cudaMemset(w->cst, 0, rt_pad * kLstmH * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->dy, rows * sizeof(float)));
+        FI_CUDA_OK(cudaMalloc((void**)&w->bias_part, ((rows + kLstmRows - 1) / kLstmRows) * kG4 * sizeof(float)));   // one row per CTA of the BPTT kernel
         FI_CUDA_OK(cudaMalloc((void**)&w->target, rows * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->d_a, rows * kFeat * sizeof(float)));
         FI_CUDA_OK(cudaMalloc((void**)&w->d_b, rows * kFeat * sizeof(float)));
@@ -395,7 +430,7 @@ static int ws_create(fi_learner* l, size_t rows, size_t t, bool training, Farmer
             FI_CUDA_OK(cudaMalloc(&w->dg_lo, rt * kG4 * 2));
             FI_CUDA_OK(cudaMalloc(&w->hp_hi, rt * kLstmH * 2));
             FI_CUDA_OK(cudaMalloc(&w->hp_lo, rt * kLstmH * 2));
-            FI_CUDA_OK(cudaMalloc((void**)&w->bias_part, (rt_pad / t / kStepBlockRows) * kG4 * sizeof(float)));
+
             size_t sw = gemm_tc_split_workspace_bytes(2, kG4, kZDim, (int)rt);
             const size_t sw2 = gemm_tc_split_workspace_bytes(2, kG4, kLstmH, (int)rt);
             if (sw2 > sw) sw = sw2;
@@ -509,8 +544,12 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         LaunchScope ls("lstm_forward_kernel", st, 2.0 * kLstmH * kG4 * (double)rt, kWorkFlops);
         static std::atomic<uint64_t> fwd_attr{0};
         FI_TRY(ensure_dynamic_smem(fwd_attr, (const void*)lstm_forward_kernel, (int)kLstmFwdSmem));
+        // training on the 3xFP16 path: h_prev leaves the kernel as the fp16 pairs the W_hh gradient product reads
+        const bool hp_pairs = half_proj && w->hp_hi;
         lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
-            w->gates, w->whh_t, params + T[3].offset, m, t, w->hprev, w->cst, w->feat);
+            w->gates, w->whh_t, params + T[3].offset, m, t, hp_pairs ? nullptr : w->hprev, w->cst, w->feat,
+            hp_pairs ? static_cast<__half*>(w->hp_hi) : nullptr, hp_pairs ? static_cast<__half*>(w->hp_lo) : nullptr,
+            hp_pairs ? w->hs + kHsHp : nullptr);
         FI_TRY(ls.done());
     }
     if (dense_tc) {
@@ -654,23 +693,19 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         LaunchScope ls("lstm_backward_kernel", st, 2.0 * kLstmH * kG4 * (double)m * t, kWorkFlops);
         static std::atomic<uint64_t> bwd_attr{0};
         FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
-        lstm_backward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset,
-                                                                                      w->cst, d, ldd, m, t);
+        const int ctas = (m + kLstmRows - 1) / kLstmRows;
+        lstm_backward_kernel<<<ctas, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset, w->cst, d, ldd, m, t,
+                                                                      farmer_use_half(l, w, rt) ? w->hs + kHsDg : nullptr, w->bias_part);
         FI_TRY(ls.done());
+        // db_ih = db_hh = the CTAs' column sums of dG, added in CTA order
+        FI_TRY(launch_lstm_bias_grad(w->bias_part, ctas, g + T[2].offset, g + T[3].offset, st));
     }
     if (farmer_use_half(l, w, rt)) {
         // dW_ih = dgates^T z, dW_hh = dgates^T h_prev: the gate gradients are split once and read MN-major by both. The
         // tensor-core recurrence has already left max |dG| and h_prev as fp16 pairs.
-        if (!lstm_tc) {
-            FI_TRY(launch_amax(w->gates, kG4, (size_t)rt, kG4, w->hs + kHsDg, st));
-            FI_TRY(launch_amax(w->hprev, kLstmH, (size_t)rt, kLstmH, w->hs + kHsHp, st));
-        }
-        if (lstm_tc) {
-            FI_TRY(launch_lstm_split_gates(w->gates, m, t, w->dg_hi, w->dg_lo, w->hs + kHsDg, st));
-        } else {
-            FI_TRY(launch_split_h(w->gates, kG4, (size_t)rt, kG4, kG4, w->dg_hi, w->dg_lo, w->hs + kHsDg, 1, st));
-            FI_TRY(launch_split_h(w->hprev, kLstmH, (size_t)rt, kLstmH, kLstmH, w->hp_hi, w->hp_lo, w->hs + kHsHp, 1, st));
-        }
+        // (both recurrent kernels have left max |dG| and h_prev as fp16 pairs)
+        if (lstm_tc) FI_TRY(launch_lstm_split_gates(w->gates, m, t, w->dg_hi, w->dg_lo, w->hs + kHsDg, st));
+        else FI_TRY(launch_split_h(w->gates, kG4, (size_t)rt, kG4, kG4, w->dg_hi, w->dg_lo, w->hs + kHsDg, 1, st));
         const SplitMat dg{w->dg_hi, w->dg_lo, kG4, w->hs + kHsDg};
         const SplitMat obs{w->obs_hi, w->obs_lo, kObsLdH, w->hs + kHsObs}, hp{w->hp_hi, w->hp_lo, kLstmH, w->hs + kHsHp};
         FI_TRY(launch_gemm_tc_split(2, kG4, kZDim, rt, dg, obs, TcOut{g + T[0].offset, kZDim, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
@@ -682,10 +717,6 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
                            0, w->gemm_ws, w->gemm_ws_bytes, st));
         FI_TRY(launch_gemm(mode, 2, kG4, kLstmH, rt, w->gates, kG4, w->hprev, kLstmH, g + T[1].offset, kLstmH, nullptr, 0,
                            nullptr, 0, w->gemm_ws, w->gemm_ws_bytes, st));
-    }
-    if (!lstm_tc) {
-        FI_TRY(launch_colsum(w->gates, kG4, rt, kG4, g + T[2].offset, w->colsum_ws, w->colsum_ws_bytes, st));
-        FI_TRY(launch_copy_words(g + T[3].offset, g + T[2].offset, kG4, st));   // d b_hh = d b_ih (a kernel: no copy engine on this stream)
     }
     return FI_OK;
 }
