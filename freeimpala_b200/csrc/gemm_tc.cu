@@ -75,6 +75,7 @@ struct TcEpilogue {
     int tma_split;       // c_hi / c_lo are written with TMA stores (map_c_hi / map_c_lo are valid)
     float* colsum_out;   // [4 * num_m_blocks, n]: column sums of the output over each warp's 32 rows (bias gradient), or null
     size_t split_stride; // elements between split-K slabs of c
+    int plain_direct;    // plain row-major fp32 output with nothing but a bias: each lane stores its row's columns as 32-byte sectors
     int step_t;          // > 0: c is the recurrent kernels' blocked gate array (lstm_tc.cu, step_block_offset): row = b * step_t + s
     int step_nblk;       //      blocks of 64 batch rows
     // 3xFP16 format only
@@ -418,8 +419,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // TMA-split epilogues take the bias through the accumulator's initial value (loaded while the first chunk is
         // still being computed) instead of 64 dependent loads per thread on the epilogue's critical path
         constexpr bool kFastSplit = H && CW == 64;   // the fp16 split epilogue below
-        const bool bias_prefetch = ep.bias != nullptr && ep.tma_split;
-        const bool bias_in_acc = bias_prefetch && !kFastSplit;   // the fp16 split epilogue adds the prefetched bias itself
+        const bool bias_prefetch = ep.bias != nullptr && (ep.tma_split || ep.plain_direct);
+        const bool bias_in_acc = bias_prefetch && !(kFastSplit && ep.tma_split);   // the fp16 split epilogue adds the prefetched bias itself
         if constexpr (H) {
             out_mul = ep.a_hs->inv * ep.b_hs->inv;
             acc_unit = ep.a_hs->scale * ep.b_hs->scale;
@@ -632,6 +633,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int i = 0; i < CW; i++) acc[i] *= out_mul;   // powers of two: exact
             }
             float* cplain = ep.c ? ep.c + (size_t)split * ep.split_stride : nullptr;
+            if (ep.plain_direct) {
+                // Plain fp32 rows (the LSTM input projection, split-K slabs of the weight gradients): the bias came through
+                // the accumulator, so the lane's 32 consecutive columns go out as four 32-byte sectors each. The transposing
+                // path below costs ~3 instructions per element; the 210 MB projection output was issue-bound on it (200 us).
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < CW / 32; c++) {
+                        const int col0 = n0 + nc0 + c * 32;
+                        float* dst = cplain + (size_t)row * ep.ldc + col0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (col0 + 8 * j < sh.n) st_global_v8u(dst + 8 * j, reinterpret_cast<const uint32_t*>(&acc[c * 32 + 8 * j]));
+                    }
+                }
+                continue;
+            }
             if (ep.transpose_out) {
                 // c[col * ldc + row]: lanes hold consecutive rows, so the register layout is already coalesced
                 if (row_ok && cplain) {
@@ -1262,6 +1279,9 @@ int launch_gemm_tc_split(int trans, int m, int n, int k, SplitMat a, SplitMat b,
     ep.mask_bits = out.mask_bits_in; ep.mask_bits_out = out.mask_bits_out; ep.mask_ldw = out.mask_ldw;
     ep.colsum_out = out.colsum_out;
     ep.step_t = out.step_t; ep.step_nblk = out.step_nblk;
+    static const bool direct_on = [] { const char* e = getenv("FI_TC_DIRECT"); return !(e && e[0] == '0'); }();
+    ep.plain_direct = direct_on && out.c && !out.c_hi && !out.transpose && !relu && !mask && !out.mask_bits_in && !out.mask_bits_out &&
+                      !out.colsum_out && out.step_t == 0 && n % 8 == 0 && out.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out.c) & 31) == 0;
     if (out.step_t > 0 && (out.c_hi || out.transpose || !out.c || relu || mask || out.mask_bits_in || out.mask_bits_out || n != 512 || m % out.step_t))
         return set_error(FI_ERR_ARG, "tcgen05 GEMM: the blocked gate-array output is a plain fp32 [b * t + s, 512] product");
     ep.a_hs = a.hs; ep.b_hs = b.hs; ep.bias_hs = bias ? out.bias_hs : nullptr; ep.out_hs = out.c_hi ? out.out_hs : nullptr;
