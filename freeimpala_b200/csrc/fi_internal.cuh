@@ -29,7 +29,7 @@ int launch_vtrace_scan(int m, int t, const float* log_rho, const float* discount
 int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar, float c_bar,
                             float pg_rho_bar, float lambda_, float baseline_cost, float entropy_cost, float* dhead,
                             float* vs, float* pg_adv, double* losses, cudaStream_t stream,
-                            float* dhead_hi = nullptr, float* dhead_lo = nullptr, int ld_split = 0);
+                            float* dhead_hi = nullptr, float* dhead_lo = nullptr, int ld_split = 0, struct HScale* dhead_hs = nullptr);
 
 // trans: 0 "NT" C = A[m,k] B[n,k]^T; 1 "NN" C = A[m,k] B[k,n]; 2 "TN" C = A[k,m]^T B[k,n].
 int launch_gemm_simt(int trans, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c,

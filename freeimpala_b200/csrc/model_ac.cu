@@ -249,10 +249,11 @@ static int ac_forward_backward_tc(fi_learner* l, Player* p, const float* batch, 
     FI_TRY(launch_gemm_tc_split(0, rows, kHead, kHid, ACT(4), W(10, kHid), TcOut{p->head, kHead, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr},
                                 p->params + T[11].offset, 0, nullptr, 0, nullptr, 0, st));
     if (!H) FI_TRY(launch_zero2(p->d_losses, 4 * sizeof(double), nullptr, 0, st));
-    if (H) {  // the loss head writes plain fp32 rows; max |x| and the fp16 split follow (13 MB)
+    if (H) {  // the loss head writes plain fp32 rows and their max |x|; the fp16 split follows (13 MB)
         FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
-                                       c.baseline_cost, c.entropy_cost, tc->dhead, nullptr, nullptr, p->d_losses, st));
-        FI_TRY(launch_amax_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, st));
+                                       c.baseline_cost, c.entropy_cost, tc->dhead, nullptr, nullptr, p->d_losses, st, nullptr, nullptr, 0,
+                                       hs + kHsDhead));
+        FI_TRY(launch_split_h(tc->dhead, kHead, (size_t)rows, kHead, kDheadLd, tc->dhead_hi, tc->dhead_lo, hs + kHsDhead, 1, st));
     } else {
         FI_TRY(launch_vtrace_loss_head(batch, m, t, p->head, kHead, c.rho_bar, c.c_bar, c.pg_rho_bar, c.lambda_,
                                        c.baseline_cost, c.entropy_cost, nullptr, nullptr, nullptr, p->d_losses, st, (float*)tc->dhead_hi,

@@ -330,8 +330,9 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
 // criterion (main.cpp:105-114) and the seed of backward: dy = dloss_i/dy / denom (mean over the
 // GLOBAL batch). losses[0] += sum_i loss_i / denom (double).
 __global__ void regression_loss_kernel(const float* __restrict__ y, const float* __restrict__ target, int m, int kind,
-                                       double inv_denom, float* __restrict__ dy, double* __restrict__ losses) {
+                                       double inv_denom, float* __restrict__ dy, double* __restrict__ losses, HScale* __restrict__ dy_hs) {
     double local = 0.0;
+    float dmax = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         const float d = y[i] - target[i];
         float g, l;
@@ -345,8 +346,14 @@ __global__ void regression_loss_kernel(const float* __restrict__ y, const float*
             g = 2.f * d;
             l = d * d;
         }
-        dy[i] = (float)((double)g * inv_denom);
+        const float dv = (float)((double)g * inv_denom);
+        dy[i] = dv;
+        dmax = fmaxf(dmax, fabsf(dv));
         local += (double)l;
+    }
+    if (dy_hs) {   // max |dy| for the fp16 split of the tensor-core backward pass
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(dmax));
+        if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&dy_hs->amax), wm);
     }
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(losses, local * inv_denom);
@@ -601,7 +608,7 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
     {
         LaunchScope ls("regression_loss_kernel", st, 12.0 * m, kWorkBytes);
         regression_loss_kernel<<<(m + 255) / 256, 256, 0, st>>>(w->y, w->target, m, l->cfg.loss, 1.0 / (double)global_m,
-                                                              w->dy, p->d_losses);
+                                                              w->dy, p->d_losses, farmer_dense_tc(l, w, m) ? w->dhs + kDhDy : nullptr);
         FI_TRY(ls.done());
     }
     float* d = w->d_a;
@@ -615,7 +622,7 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
             return SplitMat{static_cast<char*>(w->w_hi) + T[tensor].offset * 2, static_cast<char*>(w->w_lo) + T[tensor].offset * 2, ld, dhs + kDhW};
         };
         auto ACT = [&](int layer) { return SplitMat{w->act_hi[layer], w->act_lo[layer], kHid, dhs + kDhAct0 + layer}; };
-        FI_TRY(launch_amax_split_h(w->dy, 1, (size_t)m, 1, kDyLd, w->dy_hi, w->dy_lo, dhs + kDhDy, st));
+        FI_TRY(launch_split_h(w->dy, 1, (size_t)m, 1, kDyLd, w->dy_hi, w->dy_lo, dhs + kDhDy, 1, st));   // max |dy| came with the loss
         const SplitMat dy{w->dy_hi, w->dy_lo, kDyLd, dhs + kDhDy};
         GradSegTable segs;
         int splits = 1;

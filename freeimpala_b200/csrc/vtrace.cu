@@ -196,7 +196,7 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
                         float rho_bar, float c_bar, float pg_rho_bar, float lambda_, float baseline_cost,
                         float entropy_cost, float* __restrict__ dhead, float* __restrict__ vs_out,
                         float* __restrict__ adv_out, double* __restrict__ losses, float* __restrict__ dhead_hi,
-                        float* __restrict__ dhead_lo, int ld_split) {
+                        float* __restrict__ dhead_lo, int ld_split, HScale* __restrict__ dhead_hs) {
     __shared__ float s_head[kLossWarps][32 * kHead];
     __shared__ float s_out[kLossWarps][2][32 * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -209,6 +209,7 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
     const float boot = __ldg(slot + (size_t)(t - 1) * kRecWords + kWAux);
     float carry = 0.f, vs_next_chunk = boot, v_next_chunk = boot;
     double l_pg = 0.0, l_bl = 0.0, l_ent = 0.0;
+    float dmax = 0.f;
     for (int c0 = ((t - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
         const int s = c0 + lane;
         const bool valid = s < t;
@@ -291,6 +292,8 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
         }
         dv[kNumActions] = -baseline_cost * (vs - v);
         if (valid) {
+#pragma unroll
+            for (int j = 0; j < kHead; j++) dmax = fmaxf(dmax, fabsf(dv[j]));
             if (vs_out) vs_out[row] = vs;
             if (adv_out) adv_out[row] = adv;
             l_pg += (double)(-logp_a * adv);
@@ -337,6 +340,10 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
         vs_next_chunk = __shfl_sync(0xffffffffu, vs, 0);
         v_next_chunk = __shfl_sync(0xffffffffu, v, 0);
     }
+    if (dhead_hs) {   // max |dhead| for the fp16 split that follows: no separate pass over the array
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(dmax));
+        if (lane == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(&dhead_hs->amax), wm);
+    }
     l_pg = warp_sum(l_pg);
     l_bl = warp_sum(l_bl);
     l_ent = warp_sum(l_ent);
@@ -351,7 +358,7 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
 int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, int ldh, float rho_bar,
                             float c_bar, float pg_rho_bar, float lambda_, float baseline_cost,
                             float entropy_cost, float* dhead, float* vs, float* pg_adv, double* losses,
-                            cudaStream_t stream, float* dhead_hi, float* dhead_lo, int ld_split) {
+                            cudaStream_t stream, float* dhead_hi, float* dhead_lo, int ld_split, HScale* dhead_hs) {
     if (m <= 0 || t <= 0) return FI_OK;
     if (!batch || !head || (!dhead && !dhead_hi) || !losses || ldh < kHead || (dhead_hi && (!dhead_lo || ld_split < kHead)))
         return set_error(FI_ERR_ARG, "vtrace loss head: bad argument");
@@ -363,7 +370,7 @@ int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, 
                    (212.0 + (vs ? 4.0 : 0.0) + (pg_adv ? 4.0 : 0.0)) * (double)m * t, kWorkBytes);
     vtrace_loss_head_kernel<<<(m + warps - 1) / warps, 32 * warps, 0, stream>>>(
         (const float*)batch, m, t, head, ldh, rho_bar, c_bar, pg_rho_bar, lambda_, baseline_cost, entropy_cost,
-        dhead, vs, pg_adv, losses, dhead_hi, dhead_lo, ld_split);
+        dhead, vs, pg_adv, losses, dhead_hi, dhead_lo, ld_split, dhead_hs);
     return ls.done();
 }
 
