@@ -142,6 +142,10 @@ int launch_lstm_backward_tc(float* gates, const float* whh, const float* cst, co
                             float* bias_part, float* g_bih, float* g_bhh, cudaStream_t st);
 // db_ih = db_hh = sum over the BPTT kernel's CTAs (or clusters) of their column sums of dG, in index order
 int launch_lstm_bias_grad(const float* part, int nparts, float* g_bih, float* g_bhh, cudaStream_t st);
+// FI_LSTM_TRACE=1 (diagnostics): a device buffer of [128 steps][12 points] clock64 stamps written by the first thread (points
+// 0..7) and a second role (8..11) of CTA 0 of a recurrent kernel; the report prints median clocks between consecutive points
+unsigned long long* lstm_trace_buffer();
+void lstm_trace_report(const char* name, unsigned long long* dev, int steps, cudaStream_t st);
 int launch_lstm_split_gates(const float* gates, int m, int t, void* hi, void* lo, HScale* hs, cudaStream_t st);
 int launch_amax_split_params(const float* p, int n, int ld_flat, void* hi, void* lo, const float* w, int w_rows, int w_cols, int ld2,
                              void* hi2, void* lo2, HScale* hs, cudaStream_t st);

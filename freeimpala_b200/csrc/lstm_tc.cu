@@ -669,7 +669,7 @@ bool lstm_tc_enabled() {
 }
 void lstm_tc_set(int on) { g_lstm_tc.store(on, std::memory_order_relaxed); }
 
-static unsigned long long* lstm_trace_buffer() {
+unsigned long long* lstm_trace_buffer() {
     static unsigned long long* buf = [] {
         unsigned long long* p = nullptr;
         const char* e = getenv("FI_LSTM_TRACE");
@@ -679,7 +679,7 @@ static unsigned long long* lstm_trace_buffer() {
     return buf;
 }
 // median clocks between consecutive trace points (and from the last point of a step to the first of the next)
-static void lstm_trace_report(const char* name, unsigned long long* dev, int steps, cudaStream_t st) {
+void lstm_trace_report(const char* name, unsigned long long* dev, int steps, cudaStream_t st) {
     if (!dev || cudaStreamSynchronize(st) != cudaSuccess) return;
     std::vector<unsigned long long> h((size_t)kTracePoints * kTraceSteps);
     if (cudaMemcpy(h.data(), dev, h.size() * sizeof(h[0]), cudaMemcpyDeviceToHost) != cudaSuccess) return;

@@ -84,6 +84,10 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
+__device__ __forceinline__ void lstm_trace_ev(unsigned long long* tr, int s, int point) {   // FI_LSTM_TRACE (fi_internal.cuh)
+    if (tr && s < 128) tr[s * 12 + point] = clock64();
+}
+
 // out[k][j] = in[j][k] for the [512,128] recurrent weight
 __global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restrict__ wt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,7 +129,7 @@ constexpr size_t kLstmFwdSmem = ((size_t)kLstmSmemK * kG4 + kLstmRows * kG4 + kL
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, const float* __restrict__ b_hh,
                     int m, int t, float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ feat,
-                    __half* __restrict__ hp_hi, __half* __restrict__ hp_lo, HScale* __restrict__ hp_hs) {
+                    __half* __restrict__ hp_hi, __half* __restrict__ hp_lo, HScale* __restrict__ hp_hs, unsigned long long* trace) {
     extern __shared__ __align__(16) float lstm_smem[];
     float* Ws = lstm_smem;                          // [64][512]   W_hh^T rows k < 64
     float* ps = Ws + kLstmSmemK * kG4;              // [8][512]    pre-activations of this step
@@ -150,7 +154,9 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
     for (int k = 0; k < kLstmH - kLstmSmemK; k++)
         wreg[k] = __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)(kLstmSmemK + k) * kG4 + j0));
     __syncthreads();
+    unsigned long long* tr = (blockIdx.x == 0 && tid == 0) ? trace : nullptr;
     for (int s = 0; s < t; s++) {
+        lstm_trace_ev(tr, s, 0);
         float2 acc2[kLstmRows / 2][2];   // [row pair][column]: .x = row 2 rp, .y = row 2 rp + 1
         float2 gx[kLstmRows];
 #pragma unroll
@@ -174,8 +180,10 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
                 acc2[rp][1] = ffma2(hp[rp], wy, acc2[rp][1]);
             }
         };
+        lstm_trace_ev(tr, s, 1);
 #pragma unroll 8
         for (int k = 0; k < kLstmSmemK; k++) fma_k(k, *reinterpret_cast<const float2*>(Ws + k * kG4 + j0));
+        lstm_trace_ev(tr, s, 2);
 #pragma unroll
         for (int k = kLstmSmemK; k < kLstmH; k++) fma_k(k, wreg[k - kLstmSmemK]);
 #pragma unroll
@@ -183,38 +191,57 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
             const float a0 = (r & 1) ? acc2[r >> 1][0].y : acc2[r >> 1][0].x, a1 = (r & 1) ? acc2[r >> 1][1].y : acc2[r >> 1][1].x;
             *reinterpret_cast<float2*>(ps + r * kG4 + j0) = make_float2(a0 + gx[r].x, a1 + gx[r].y);
         }
+        lstm_trace_ev(tr, s, 3);
         __syncthreads();
-        // (row, unit) pairs: 8 * 128 = 1024 over 256 threads
-        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-            const int r = i / kLstmH, u = i % kLstmH;
-            float h = 0.f;
+        lstm_trace_ev(tr, s, 4);
+        // (row, unit) pairs: 8 * 128 = 1024 over 256 threads = 4 per thread (unit tid % 128, rows tid / 128 + 2 k). All loads
+        // first, then the four gate chains side by side, then the stores: written pair by pair the shared-memory stores of one
+        // pair ordered the loads of the next behind them and the phase took 3200 clocks of exposed latency per step. A pair's
+        // h_{s-1} entry in hs is read by its own thread only (the product is done), so h_s goes straight back into it.
+        constexpr int kPairs = kLstmRows * kLstmH / kLstmThreads;
+        float pin[kPairs][4], cin[kPairs], hin[kPairs];
+#pragma unroll
+        for (int k = 0; k < kPairs; k++) {
+            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+#pragma unroll
+            for (int g = 0; g < 4; g++) pin[k][g] = ps[r * kG4 + g * kLstmH + u];
+            cin[k] = cs[r * kLstmH + u];
+            hin[k] = hs[u * kLstmRows + r];
+        }
+        float gv[kPairs][4], cv[kPairs], hv[kPairs];
+#pragma unroll
+        for (int k = 0; k < kPairs; k++) {
+            gv[k][0] = sigmoidf_(pin[k][0]);
+            gv[k][1] = sigmoidf_(pin[k][1]);
+            gv[k][2] = tanhf(pin[k][2]);
+            gv[k][3] = sigmoidf_(pin[k][3]);
+            cv[k] = fmaf(gv[k][1], cin[k], gv[k][0] * gv[k][2]);
+            hv[k] = gv[k][3] * tanhf(cv[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kPairs; k++) {
+            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
             if (r < nrows) {
-                const float ig = sigmoidf_(ps[r * kG4 + u]), fg = sigmoidf_(ps[r * kG4 + kLstmH + u]);
-                const float gg = tanhf(ps[r * kG4 + 2 * kLstmH + u]), og = sigmoidf_(ps[r * kG4 + 3 * kLstmH + u]);
-                const float c = fmaf(fg, cs[r * kLstmH + u], ig * gg);
-                h = og * tanhf(c);
                 const size_t row = (size_t)(b0 + r) * t + s;
                 float* g = gates + row * kG4;
-                g[u] = ig; g[kLstmH + u] = fg; g[2 * kLstmH + u] = gg; g[3 * kLstmH + u] = og;
-                if (cst) cst[row * kLstmH + u] = c;
-                if (hprev) hprev[row * kLstmH + u] = hs[u * kLstmRows + r];   // h_{s-1}
+                g[u] = gv[k][0]; g[kLstmH + u] = gv[k][1]; g[2 * kLstmH + u] = gv[k][2]; g[3 * kLstmH + u] = gv[k][3];
+                if (cst) cst[row * kLstmH + u] = cv[k];
+                if (hprev) hprev[row * kLstmH + u] = hin[k];   // h_{s-1}
                 if (hp_hi) {   // ... or directly as the fp16 pair the W_hh gradient product reads
-                    const float hv = hs[u * kLstmRows + r] * kHprevScale;
-                    const __half hh = __float2half_rn(hv);
+                    const float x = hin[k] * kHprevScale;
+                    const __half hh = __float2half_rn(x);
                     hp_hi[row * kLstmH + u] = hh;
-                    hp_lo[row * kLstmH + u] = __float2half_rn((hv - __half2float(hh)) * 2048.f);
+                    hp_lo[row * kLstmH + u] = __float2half_rn((x - __half2float(hh)) * 2048.f);
                 }
-                cs[r * kLstmH + u] = c;
-                if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = h;
+                if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = hv[k];
             }
-            ps[r * kG4 + u] = h;  // parked: hs is still being read as h_{s-1} by other pairs of this pass
+            cs[r * kLstmH + u] = r < nrows ? cv[k] : 0.f;
+            hs[u * kLstmRows + r] = r < nrows ? hv[k] : 0.f;
         }
+        lstm_trace_ev(tr, s, 5);
         __syncthreads();
-        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-            const int r = i / kLstmH, u = i % kLstmH;
-            hs[u * kLstmRows + r] = ps[r * kG4 + u];
-        }
-        __syncthreads();
+        lstm_trace_ev(tr, s, 6);
+        lstm_trace_ev(tr, s, 7);
     }
 }
 
@@ -224,29 +251,60 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
 // partial sums are combined through shared memory. W_hh stays on chip: the first 64 gate rows of every quarter
 // (128 KB) in shared memory, the other 64 in registers (128 per thread).
 constexpr int kLstmSmemJ = 256;
-constexpr size_t kLstmBwdSmem = ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 2 * kLstmRows * kLstmH + 4 * kLstmRows * kLstmH) * sizeof(float);
+constexpr int kLstmBwdPre = 6;   // per (row, unit) pair and step: gates i, f, g, o, c_s, c_{s-1}, prefetched one step ahead
+constexpr size_t kLstmBwdSmem =
+    ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 2 * kLstmRows * kLstmH + 4 * kLstmRows * kLstmH + kLstmBwdPre * kLstmRows * kLstmH) * sizeof(float);
 
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
-                     const float* __restrict__ dfeat, int ldf, int m, int t, HScale* __restrict__ dg_hs, float* __restrict__ bias_part) {
+                     const float* __restrict__ dfeat, int ldf, int m, int t, HScale* __restrict__ dg_hs, float* __restrict__ bias_part,
+                     unsigned long long* trace) {
     extern __shared__ __align__(16) float lstm_smem[];
     float* Wh = lstm_smem;                          // [4][64][128] W_hh rows 128q + jj, jj < 64
     float* dgs = Wh + kLstmSmemJ * kLstmH;          // [512][8]    dG of this step, j-major
     float* dh = dgs + kG4 * kLstmRows;              // [8][128]
     float* dc = dh + kLstmRows * kLstmH;            // [8][128]
     float* part = dc + kLstmRows * kLstmH;          // [4][8][128]
+    float* pre = part + 4 * kLstmRows * kLstmH;     // [6][8][128] next step's operands of the element-wise part
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kLstmRows;
     const int nrows = min(kLstmRows, m - b0);
+    // The element-wise part of a step reads 6 values per (row, unit) pair from global memory; loaded where they are used
+    // they cost 4900 clocks of exposed latency per step (41 % of the step, clock64 trace). Each thread fetches ITS pairs'
+    // operands of step s-1 with cp.async while the dh product of step s runs; it is also the only reader of those entries.
+    auto prefetch = [&](int s) {
+#pragma unroll
+        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
+            const int r = i / kLstmH, u = i % kLstmH;
+            if (r < nrows) {
+                const size_t row = (size_t)(b0 + r) * t + s;
+                const float* g = gates + row * kG4 + u;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pre + i);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + j * kLstmRows * kLstmH * 4), "l"(g + j * kLstmH) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * kLstmRows * kLstmH * 4), "l"(cst + row * kLstmH + u) : "memory");
+                if (s > 0)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 5 * kLstmRows * kLstmH * 4), "l"(cst + (row - 1) * kLstmH + u)
+                                 : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t - 1);
     for (int i = tid; i < kLstmSmemJ * kLstmH / 4; i += kLstmThreads) {
         const int row = i / (kLstmH / 4), c4 = i % (kLstmH / 4);       // smem row = 64 * quarter + jj
         const int j = (row >> 6) * kLstmH + (row & 63);
         reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * kLstmH) + c4);
     }
-    for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-        const int r = i / kLstmH, u = i % kLstmH;
-        dh[i] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
-        dc[i] = 0.f;
+    // dL/dh and dL/dc of this thread's 4 (row, unit) pairs live in registers: every pass over the pairs uses the same mapping
+    constexpr int kPairs = kLstmRows * kLstmH / kLstmThreads;
+    float dhr[kPairs], dcr[kPairs];
+#pragma unroll
+    for (int k = 0; k < kPairs; k++) {
+        const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+        dhr[k] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
+        dcr[k] = 0.f;
     }
     const int q = tid >> 6, k0 = (tid & 63) * 2;
     float2 wreg[64];
@@ -256,33 +314,47 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
     // max |dG| (for the fp16 split that follows) and this CTA's column sums of dG (the bias gradient): thread tid always
     // meets unit tid % 128, rows tid / 128 + 2 k
     float run_max = 0.f, bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
+    unsigned long long* tr = (blockIdx.x == 0 && tid == 0) ? trace : nullptr;
     for (int s = t - 1; s >= 0; s--) {
-        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-            const int r = i / kLstmH, u = i % kLstmH;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-            if (r < nrows) {
-                const size_t row = (size_t)(b0 + r) * t + s;
-                float* g = gates + row * kG4;
-                const float ig = g[u], fg = g[kLstmH + u], gg = g[2 * kLstmH + u], og = g[3 * kLstmH + u];
-                const float tc = tanhf(cst[row * kLstmH + u]);
-                const float cp = s > 0 ? cst[(row - 1) * kLstmH + u] : 0.f;
-                const float dhv = dh[i];
-                const float dct = dc[i] + dhv * og * (1.f - tc * tc);
-                d0 = dct * gg * ig * (1.f - ig);
-                d1 = dct * cp * fg * (1.f - fg);
-                d2 = dct * ig * (1.f - gg * gg);
-                d3 = dhv * tc * og * (1.f - og);
-                g[u] = d0; g[kLstmH + u] = d1; g[2 * kLstmH + u] = d2; g[3 * kLstmH + u] = d3;
-                dc[i] = dct * fg;
-                run_max = fmaxf(fmaxf(run_max, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
-                bs0 += d0; bs1 += d1; bs2 += d2; bs3 += d3;
-            }
-            dgs[u * kLstmRows + r] = d0;
-            dgs[(kLstmH + u) * kLstmRows + r] = d1;
-            dgs[(2 * kLstmH + u) * kLstmRows + r] = d2;
-            dgs[(3 * kLstmH + u) * kLstmRows + r] = d3;
+        lstm_trace_ev(tr, t - 1 - s, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's operands of step s have landed
+        float pv[kLstmRows * kLstmH / kLstmThreads][kLstmBwdPre];
+#pragma unroll
+        for (int k = 0; k < kLstmRows * kLstmH / kLstmThreads; k++)
+#pragma unroll
+            for (int j = 0; j < kLstmBwdPre; j++) pv[k][j] = pre[j * kLstmRows * kLstmH + tid + k * kLstmThreads];
+        if (s > 0) prefetch(s - 1);   // rows of step s-1: disjoint from the rows of step s written below
+        float dd[kPairs][4];
+#pragma unroll   // the four chains side by side: every operand is in registers
+        for (int k = 0; k < kPairs; k++) {
+            const float ig = pv[k][0], fg = pv[k][1], gg = pv[k][2], og = pv[k][3];
+            const float tc = tanhf(pv[k][4]);
+            const float cp = s > 0 ? pv[k][5] : 0.f;
+            const float dct = dcr[k] + dhr[k] * og * (1.f - tc * tc);
+            dd[k][0] = dct * gg * ig * (1.f - ig);
+            dd[k][1] = dct * cp * fg * (1.f - fg);
+            dd[k][2] = dct * ig * (1.f - gg * gg);
+            dd[k][3] = dhr[k] * tc * og * (1.f - og);
+            dcr[k] = dct * fg;
         }
+#pragma unroll
+        for (int k = 0; k < kPairs; k++) {
+            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+            if (r < nrows) {
+                float* g = gates + ((size_t)(b0 + r) * t + s) * kG4;
+                g[u] = dd[k][0]; g[kLstmH + u] = dd[k][1]; g[2 * kLstmH + u] = dd[k][2]; g[3 * kLstmH + u] = dd[k][3];
+                run_max = fmaxf(fmaxf(run_max, fmaxf(fabsf(dd[k][0]), fabsf(dd[k][1]))), fmaxf(fabsf(dd[k][2]), fabsf(dd[k][3])));
+                bs0 += dd[k][0]; bs1 += dd[k][1]; bs2 += dd[k][2]; bs3 += dd[k][3];
+            } else {
+                dd[k][0] = dd[k][1] = dd[k][2] = dd[k][3] = 0.f;   // rows beyond the batch (their operands were never fetched)
+                dcr[k] = 0.f;
+            }
+#pragma unroll
+            for (int g4 = 0; g4 < 4; g4++) dgs[(g4 * kLstmH + u) * kLstmRows + r] = dd[k][g4];
+        }
+        lstm_trace_ev(tr, t - 1 - s, 1);
         __syncthreads();
+        lstm_trace_ev(tr, t - 1 - s, 2);
         if (s > 0) {  // dh_{s-1}[r][k] = sum_j dG[r][j] W_hh[j][k]
             float2 acc2[kLstmRows / 2][2];   // [row pair][column]
 #pragma unroll
@@ -300,16 +372,24 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
             };
 #pragma unroll 8
             for (int jj = 0; jj < 64; jj++) fma_j(q * kLstmH + jj, *reinterpret_cast<const float2*>(Wh + (q * 64 + jj) * kLstmH + k0));
+            lstm_trace_ev(tr, t - 1 - s, 3);
 #pragma unroll
             for (int jj = 0; jj < 64; jj++) fma_j(q * kLstmH + 64 + jj, wreg[jj]);
+            lstm_trace_ev(tr, t - 1 - s, 4);
 #pragma unroll
             for (int r = 0; r < kLstmRows; r++)
                 *reinterpret_cast<float2*>(part + (q * kLstmRows + r) * kLstmH + k0) =
                     make_float2((r & 1) ? acc2[r >> 1][0].y : acc2[r >> 1][0].x, (r & 1) ? acc2[r >> 1][1].y : acc2[r >> 1][1].x);
+            lstm_trace_ev(tr, t - 1 - s, 5);
             __syncthreads();
-            for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads)
-                dh[i] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
-            __syncthreads();
+            lstm_trace_ev(tr, t - 1 - s, 6);
+#pragma unroll
+            for (int k = 0; k < kPairs; k++) {
+                const int i = tid + k * kLstmThreads;
+                dhr[k] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
+            }
+            // (no barrier here: `part` is next written after the barrier that follows the next step's element-wise part)
+            lstm_trace_ev(tr, t - 1 - s, 7);
         }
     }
     if (dg_hs) {
@@ -556,8 +636,9 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
             w->gates, w->whh_t, params + T[3].offset, m, t, hp_pairs ? nullptr : w->hprev, w->cst, w->feat,
             hp_pairs ? static_cast<__half*>(w->hp_hi) : nullptr, hp_pairs ? static_cast<__half*>(w->hp_lo) : nullptr,
-            hp_pairs ? w->hs + kHsHp : nullptr);
+            hp_pairs ? w->hs + kHsHp : nullptr, lstm_trace_buffer());
         FI_TRY(ls.done());
+        lstm_trace_report("forward (FFMA)", lstm_trace_buffer(), t, st);
     }
     if (dense_tc) {
         // x_l = relu(x_{l-1} W_l^T + b_l), written as fp16 pairs (and ReLU bit masks) by the GEMM epilogue; y = x_5 w_6 + b_6
@@ -702,8 +783,10 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
         const int ctas = (m + kLstmRows - 1) / kLstmRows;
         lstm_backward_kernel<<<ctas, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset, w->cst, d, ldd, m, t,
-                                                                      farmer_use_half(l, w, rt) ? w->hs + kHsDg : nullptr, w->bias_part);
+                                                                      farmer_use_half(l, w, rt) ? w->hs + kHsDg : nullptr, w->bias_part,
+                                                                      lstm_trace_buffer());
         FI_TRY(ls.done());
+        lstm_trace_report("backward (FFMA)", lstm_trace_buffer(), t, st);
         // db_ih = db_hh = the CTAs' column sums of dG, added in CTA order
         FI_TRY(launch_lstm_bias_grad(w->bias_part, ctas, g + T[2].offset, g + T[3].offset, st));
     }
