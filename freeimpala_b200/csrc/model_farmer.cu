@@ -71,7 +71,29 @@ enum { kDhW = 0, kDhFeat = 1, kDhDy = 2, kDhAct0 = 3, kDhD0 = 8, kDhCount = 14 }
 constexpr int kObsLdH = 192;   // 162 observation words padded to three whole 128-byte lines of fp16 (see model_ac.cu)
 enum { kHsObs = 0, kHsWih = 1, kHsDg = 2, kHsHp = 3 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Branch-free gate functions for the recurrent kernels. The library expf / tanhf / IEEE division carry range checks and
+// (tanhf) a data-dependent branch that a warp of 32 different pre-activations takes both ways; the element-wise part of a
+// step is a chain of five of them per (row, unit) pair and was 3100 clocks of a 9500-clock step (clock64 trace).
+//   e^x: ex2.approx of x * log2(e) with the rounding error of that product (and of the constant) fed back as a first-order
+//        correction: ~2 ulp, the error class of expf itself;
+//   sigmoid: one approximate reciprocal (1 ulp);
+//   tanh: |x| >= 0.25: 1 - 2 / (e^{2|x|} + 1) (absolute error ~1e-7, i.e. <= 5e-7 relative there);
+//         |x| <  0.25: odd Taylor polynomial to x^9 (next term < 1e-8 relative).
+__device__ __forceinline__ float fast_exp(float x) {
+    const float t = x * 1.44269502f;
+    const float r = fmaf(x, 1.44269502f, -t) + x * 1.925963033e-8f;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e * fmaf(r, 0.693147182f, 1.f);   // (not e + e * r ln 2: e may be +inf)
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + fast_exp(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float ax = fabsf(x), x2 = ax * ax;
+    const float big = 1.f - __fdividef(2.f, fast_exp(2.f * ax) + 1.f);
+    const float poly = fmaf(x2, fmaf(x2, fmaf(x2, 0.0218694885f, -0.0539682540f), 0.133333333f), -0.333333333f);
+    const float small = fmaf(ax * x2, poly, ax);
+    return copysignf(ax < 0.25f ? small : big, x);
+}
 
 // Two fp32 FMAs in one instruction (sm_100 FFMA2; bit-identical to two fmaf's). With b = {w, w} ptxas emits the scalar-broadcast
 // form (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2), so a row pair of the recurrent products costs one issue slot instead of two.
@@ -213,10 +235,10 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         for (int k = 0; k < kPairs; k++) {
             gv[k][0] = sigmoidf_(pin[k][0]);
             gv[k][1] = sigmoidf_(pin[k][1]);
-            gv[k][2] = tanhf(pin[k][2]);
+            gv[k][2] = fast_tanh(pin[k][2]);
             gv[k][3] = sigmoidf_(pin[k][3]);
             cv[k] = fmaf(gv[k][1], cin[k], gv[k][0] * gv[k][2]);
-            hv[k] = gv[k][3] * tanhf(cv[k]);
+            hv[k] = gv[k][3] * fast_tanh(cv[k]);
         }
 #pragma unroll
         for (int k = 0; k < kPairs; k++) {
@@ -328,7 +350,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
 #pragma unroll   // the four chains side by side: every operand is in registers
         for (int k = 0; k < kPairs; k++) {
             const float ig = pv[k][0], fg = pv[k][1], gg = pv[k][2], og = pv[k][3];
-            const float tc = tanhf(pv[k][4]);
+            const float tc = fast_tanh(pv[k][4]);
             const float cp = s > 0 ? pv[k][5] : 0.f;
             const float dct = dcr[k] + dhr[k] * og * (1.f - tc * tc);
             dd[k][0] = dct * gg * ig * (1.f - ig);
