@@ -216,19 +216,25 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         lstm_trace_ev(tr, s, 3);
         __syncthreads();
         lstm_trace_ev(tr, s, 4);
-        // (row, unit) pairs: 8 * 128 = 1024 over 256 threads = 4 per thread (unit tid % 128, rows tid / 128 + 2 k). All loads
+        // (row, unit) pairs: 8 * 128 = 1024 over 256 threads = 4 per thread: unit tid % 128, rows 4 (tid / 128) + k, so that a
+        // thread's entries of the k-major hs array ([unit][8 rows]) are one 16-byte vector (scalar accesses, 32 bytes apart from
+        // lane to lane, were 8-way bank conflicts). All loads
         // first, then the four gate chains side by side, then the stores: written pair by pair the shared-memory stores of one
         // pair ordered the loads of the next behind them and the phase took 3200 clocks of exposed latency per step. A pair's
         // h_{s-1} entry in hs is read by its own thread only (the product is done), so h_s goes straight back into it.
         constexpr int kPairs = kLstmRows * kLstmH / kLstmThreads;
         float pin[kPairs][4], cin[kPairs], hin[kPairs];
 #pragma unroll
+        const int u = tid & (kLstmH - 1), r4 = (tid >> 7) * kPairs;   // this thread's unit and first row
         for (int k = 0; k < kPairs; k++) {
-            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+            const int r = r4 + k;
 #pragma unroll
             for (int g = 0; g < 4; g++) pin[k][g] = ps[r * kG4 + g * kLstmH + u];
             cin[k] = cs[r * kLstmH + u];
-            hin[k] = hs[u * kLstmRows + r];
+        }
+        {
+            const float4 h4 = *reinterpret_cast<const float4*>(hs + u * kLstmRows + r4);
+            hin[0] = h4.x; hin[1] = h4.y; hin[2] = h4.z; hin[3] = h4.w;
         }
         float gv[kPairs][4], cv[kPairs], hv[kPairs];
 #pragma unroll
@@ -242,7 +248,7 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         }
 #pragma unroll
         for (int k = 0; k < kPairs; k++) {
-            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+            const int r = r4 + k;
             if (r < nrows) {
                 const size_t row = (size_t)(b0 + r) * t + s;
                 float* g = gates + row * kG4;
@@ -258,8 +264,9 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
                 if (s == t - 1) feat[(size_t)(b0 + r) * kFeat + u] = hv[k];
             }
             cs[r * kLstmH + u] = r < nrows ? cv[k] : 0.f;
-            hs[u * kLstmRows + r] = r < nrows ? hv[k] : 0.f;
+            if (r >= nrows) hv[k] = 0.f;
         }
+        *reinterpret_cast<float4*>(hs + u * kLstmRows + r4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
         lstm_trace_ev(tr, s, 5);
         __syncthreads();
         lstm_trace_ev(tr, s, 6);
@@ -294,10 +301,11 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
     // The element-wise part of a step reads 6 values per (row, unit) pair from global memory; loaded where they are used
     // they cost 4900 clocks of exposed latency per step (41 % of the step, clock64 trace). Each thread fetches ITS pairs'
     // operands of step s-1 with cp.async while the dh product of step s runs; it is also the only reader of those entries.
+    const int u = tid & (kLstmH - 1), r4 = (tid >> 7) * (kLstmRows * kLstmH / kLstmThreads);   // this thread's unit and first of its 4 rows
     auto prefetch = [&](int s) {
 #pragma unroll
-        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {
-            const int r = i / kLstmH, u = i % kLstmH;
+        for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) {   // i: the thread's private slots of `pre`
+            const int r = r4 + i / kLstmThreads;
             if (r < nrows) {
                 const size_t row = (size_t)(b0 + r) * t + s;
                 const float* g = gates + row * kG4 + u;
@@ -319,12 +327,12 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
         const int j = (row >> 6) * kLstmH + (row & 63);
         reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * kLstmH) + c4);
     }
-    // dL/dh and dL/dc of this thread's 4 (row, unit) pairs live in registers: every pass over the pairs uses the same mapping
+    // dL/dh and dL/dc of this thread's 4 (row, unit) pairs (unit tid % 128, rows 4 (tid / 128) + k) live in registers
     constexpr int kPairs = kLstmRows * kLstmH / kLstmThreads;
     float dhr[kPairs], dcr[kPairs];
 #pragma unroll
     for (int k = 0; k < kPairs; k++) {
-        const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+        const int r = r4 + k;
         dhr[k] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
         dcr[k] = 0.f;
     }
@@ -334,7 +342,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
     for (int jj = 0; jj < 64; jj++) wreg[jj] = __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + 64 + jj) * kLstmH + k0));
     __syncthreads();
     // max |dG| (for the fp16 split that follows) and this CTA's column sums of dG (the bias gradient): thread tid always
-    // meets unit tid % 128, rows tid / 128 + 2 k
+    // meets unit tid % 128 (rows 4 (tid / 128) + k)
     float run_max = 0.f, bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
     unsigned long long* tr = (blockIdx.x == 0 && tid == 0) ? trace : nullptr;
     for (int s = t - 1; s >= 0; s--) {
@@ -361,7 +369,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
         }
 #pragma unroll
         for (int k = 0; k < kPairs; k++) {
-            const int i = tid + k * kLstmThreads, r = i / kLstmH, u = i % kLstmH;
+            const int r = r4 + k;
             if (r < nrows) {
                 float* g = gates + ((size_t)(b0 + r) * t + s) * kG4;
                 g[u] = dd[k][0]; g[kLstmH + u] = dd[k][1]; g[2 * kLstmH + u] = dd[k][2]; g[3 * kLstmH + u] = dd[k][3];
@@ -371,9 +379,10 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
                 dd[k][0] = dd[k][1] = dd[k][2] = dd[k][3] = 0.f;   // rows beyond the batch (their operands were never fetched)
                 dcr[k] = 0.f;
             }
-#pragma unroll
-            for (int g4 = 0; g4 < 4; g4++) dgs[(g4 * kLstmH + u) * kLstmRows + r] = dd[k][g4];
         }
+#pragma unroll   // the thread's 4 rows of a gate column: one 16-byte store into the j-major dgs array
+        for (int g4 = 0; g4 < 4; g4++)
+            *reinterpret_cast<float4*>(dgs + (g4 * kLstmH + u) * kLstmRows + r4) = make_float4(dd[0][g4], dd[1][g4], dd[2][g4], dd[3][g4]);
         lstm_trace_ev(tr, t - 1 - s, 1);
         __syncthreads();
         lstm_trace_ev(tr, t - 1 - s, 2);
@@ -407,7 +416,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
             lstm_trace_ev(tr, t - 1 - s, 6);
 #pragma unroll
             for (int k = 0; k < kPairs; k++) {
-                const int i = tid + k * kLstmThreads;
+                const int i = (r4 + k) * kLstmH + u;
                 dhr[k] = (part[i] + part[kLstmRows * kLstmH + i]) + (part[2 * kLstmRows * kLstmH + i] + part[3 * kLstmRows * kLstmH + i]);
             }
             // (no barrier here: `part` is next written after the barrier that follows the next step's element-wise part)
