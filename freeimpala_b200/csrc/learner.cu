@@ -1139,6 +1139,7 @@ int fi_learner_debug_relu_masks(fi_learner* l, int player, unsigned char* host, 
 void fi_prof_enable(int on) {
     fi::ProfState& p = fi::prof();
     std::lock_guard<std::mutex> g(p.mu);
+    if (!on) p.close_locked();
     p.on.store(on != 0);
 }
 
@@ -1147,6 +1148,7 @@ int fi_prof_collect(fi_prof_entry* out, int max_entries) {
     std::vector<fi::ProfRec> recs;
     {
         std::lock_guard<std::mutex> g(p.mu);
+        p.close_locked();
         recs.swap(p.recs);
     }
     std::vector<fi_prof_entry> agg;
@@ -1165,7 +1167,7 @@ int fi_prof_collect(fi_prof_entry* out, int max_entries) {
             agg.push_back(n);
             e = &agg.back();
         }
-        e->launches++;
+        e->launches += (uint64_t)r.launches;
         e->total_ms += ms;
         e->work += r.work;
     }
