@@ -392,6 +392,30 @@ def test_farmer_step_through_ring_decodes_records(fi, oracle):
     L.close()
 
 
+def test_profiler_brackets_account_for_every_launch(fi):
+    """fi_prof_enable / fi_prof_collect (what bench.py's per-kernel rooflines are made of): consecutive launches of one
+    kernel share an event bracket, yet every launch is counted, every kernel gets a positive time and its work tag."""
+    m, t = 4, 7
+    L = _ac_learner(fi, m, t, gemm_mode="simt")
+    batch = L.stage_batch(0, po.pack_vtrace_slots(*U.vtrace_batch(5, m, t)))
+    L.trainModel(0, batch)
+    L.sync(0)
+    fi.prof_collect()
+    fi.prof_enable(True)
+    n0 = fi.kernel_launch_count()
+    for _ in range(3):   # (graphs are not used while the profiler is on)
+        L.trainModel(0, batch)
+    L.sync(0)
+    fi.prof_enable(False)
+    launched = fi.kernel_launch_count() - n0
+    prof = fi.prof_collect()
+    assert launched > 0 and sum(r["launches"] for r in prof.values()) == launched
+    assert all(r["total_ms"] > 0 and r["work"] > 0 for r in prof.values())
+    assert prof["gemm_simt_kernel"]["launches"] % 3 == 0 and prof["fused_opt_kernel"]["launches"] == 3
+    assert fi.prof_collect() == {}   # the window was reset
+    L.close()
+
+
 def test_losses_at_reads_back_any_of_the_last_steps(fi):
     """fi_learner_losses_at: per-step loss read-back ring (a host loop logs step s-1 while step s runs)."""
     m, t = 3, 6
