@@ -377,8 +377,13 @@ def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: b
         e2e_losses = []
         host_ms = {"readBatch": 0.0, "trainModel": 0.0}
 
-        def e2e_steps(steps: int, writer, nw: int):
+        def e2e_steps(steps: int, writer, nw: int, lead: int = 0):
+            """`steps` learner steps fed by `nw` producer threads. Returns the time from the moment the loss of step `lead`
+            - 1 has reached the host to the moment the loss of the last step has: the steps [lead, steps) in the steady state
+            of the producer -> H2D -> gather -> step pipeline (lead = 0: from the call, thread start-up and pipeline fill
+            included)."""
             ts = [threading.Thread(target=writer, args=(j, steps, nw)) for j in range(nw)]
+            t_start = time.perf_counter()
             for t in ts:
                 t.start()
             base = L.steps_done(0)
@@ -395,27 +400,34 @@ def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: b
                 # stream never drains between steps, and the last step's after the loop
                 if s > 0:
                     e2e_losses.append(L.losses_at(0, base + s)[0])
+                if s == lead and lead > 0:
+                    t_start = time.perf_counter()   # the loss of step lead - 1 is on the host
             e2e_losses.append(L.losses_at(0, base + steps)[0])
+            t_end = time.perf_counter()
             for t in ts:
                 t.join()
+            return t_end - t_start
+
+        E2E_LEAD = 3   # untimed steps of the SAME continuous run in front of the K timed ones (producer threads started,
+                       # ring filled, the pipeline in its steady state: bench.py's W warm-up steps, for the e2e loop)
 
         def timed(writer, nw):
             L.sync(0)
             job.barrier()
             torch.cuda.synchronize()
-            t0, tw0 = time.perf_counter(), time.time()
-            e2e_steps(K, writer, nw)
+            tw0 = time.time()
+            dt = e2e_steps(E2E_LEAD + K, writer, nw, lead=E2E_LEAD)
             L.sync(0)
             torch.cuda.synchronize()
-            t1, tw1 = time.perf_counter(), time.time()
+            tw1 = time.time()
             job.barrier()
             windows.append((tw0, tw1))
-            return job.max_over_ranks(t1 - t0)
+            return job.max_over_ranks(dt)
 
         e2e_steps(max(W, 4), copy_writer, nw_copy)   # warm-up; also leaves a valid trajectory in each pinned slot
         host_ms.update(readBatch=0.0, trainModel=0.0)
         copy_s = timed(copy_writer, nw_copy)
-        copy_host = {k: v / K for k, v in host_ms.items()}   # rank 0's host time per step inside the two calls (blocking included)
+        copy_host = {k: v / (E2E_LEAD + K) for k, v in host_ms.items()}   # rank 0's host time per step inside the two calls (blocking included)
         zc_s = timed(inplace_writer, nw_zc)
         res["e2e"] = {
             "value": world * M * T * K / copy_s, "unit": UNIT, "ms_per_step": copy_s / K * 1e3,
@@ -424,7 +436,10 @@ def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: b
             "path": f"{nw_copy} actor threads per rank call SharedBuffer::write semantics (fi_ring_write_many: every byte of every "
                     f"trajectory is copied from the actor's buffer into a pinned ring slot) -> cudaMemcpyAsync per run of slots on the "
                     f"side stream -> readBatch (gather kernel) -> Learner.trainModel -> losses D2H every step; weights published D2H "
-                    f"every step; the loss of step s is read by the host while step s+1 runs (fi_learner_losses_at)",
+                    f"every step; the loss of step s is read by the host while step s+1 runs (fi_learner_losses_at). Timed: "
+                    f"{K} consecutive steps of one continuous run, from the moment the loss of the step before them has reached the "
+                    f"host to the moment the loss of the last one has ({E2E_LEAD} untimed steps of the same run in front: producer "
+                    f"threads started, ring filled); every timed step's H2D copy and loss read-back fall inside the region",
             "losses_read": len(e2e_losses), "host_ms_per_step": copy_host,
             "inplace": {"value": world * M * T * K / zc_s, "ms_per_step": zc_s / K * 1e3, "producer_threads": nw_zc,
                         "path": "zero-copy producer API (fi_ring_reserve_many / fi_ring_commit_many): the trajectory already sits in the "
