@@ -220,6 +220,25 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(torch, local: int):
+    """sched_setaffinity to the CPUs NVML reports as local to CUDA device `local` (matched by PCI bus id); None if NVML, the
+    device or the cpuset does not allow it."""
+    try:
+        import pynvml
+        pr = torch.cuda.get_device_properties(local)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return {"cpus": len(after), "of": len(before)}
+    except Exception:   # no NVML, no permission, CPUs outside the cpuset: stay where the launcher put us
+        return None
+
+
 class Job:
     """Process-wide state of the b200 arm: rank / world, torch, barriers, reductions over ranks."""
 
@@ -239,6 +258,13 @@ class Job:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local)
+        # Several ranks on one node: keep this rank's threads (actor threads included: they inherit it) and therefore its
+        # pinned ring (first touch) on the CPUs next to its GPU, as a deployment would (numactl / the launcher's binding).
+        # FI_BENCH_NUMA=0 leaves the process where the launcher put it.
+        self.cpu_binding = None
+        self.total_cores = host_cores()   # before any binding: what the node gives the whole job
+        if self.world > 1 and os.environ.get("FI_BENCH_NUMA", "1") != "0":
+            self.cpu_binding = bind_to_gpu_cpus(torch, self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
@@ -347,7 +373,7 @@ def measure(job: Job, args, workload: str, M: int, windows: list, *, with_e2e: b
     # ---------------- e2e: host buffers through SharedBuffer.write -> trainModel -> loss read-back ---
     if with_e2e:
         ring = L.getSharedBuffers()[0]
-        cores_per_rank = max(1, host_cores() // world)
+        cores_per_rank = max(1, job.total_cores // world)
         nw_copy = args.writers if args.writers > 0 else max(2, min(14, cores_per_rank - 2))
         nw_zc = int(os.environ.get("FI_BENCH_ZC_THREADS", "2"))  # in-place producers only take the ring lock: two threads keep the ring full
         zc_burst = int(os.environ.get("FI_BENCH_ZC_BURST", "64"))
@@ -589,7 +615,7 @@ def run_b200_arm(args):
                           "l2": "inputs (105 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
                           "flops_per_step": None if farmer else 3.0 * AC_FWD_FLOPS_PER_TRANSITION * M * T},
                "gpu_launches": int(launches), "ms_per_step_instrumented": main["ms_per_step_prof"],
-               "ms_per_step_by_rank": main["per_rank_ms"], "clocks": clocks, "e2e": main["e2e"], "roofline": roofline, "kernels": kernels,
+               "ms_per_step_by_rank": main["per_rank_ms"], "clocks": clocks, "cpu_binding": job.cpu_binding, "e2e": main["e2e"], "roofline": roofline, "kernels": kernels,
                "cpu_baseline": cpu, "losses_last_step": main["losses"],
                "reference_workload": wl_block(ref_wl, f"farmer_lstm MSE/Adam learner step (cmd/libtorch_bench train_step), batch {M} x T={T} "
                                                       f"per GPU: the configuration `bench.py --impl reference` times on the CPU"),
