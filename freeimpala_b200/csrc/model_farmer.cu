@@ -282,7 +282,7 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
 constexpr int kLstmSmemJ = 256;
 constexpr int kLstmBwdPre = 6;   // per (row, unit) pair and step: gates i, f, g, o, c_s, c_{s-1}, prefetched one step ahead
 constexpr size_t kLstmBwdSmem =
-    ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 2 * kLstmRows * kLstmH + 4 * kLstmRows * kLstmH + kLstmBwdPre * kLstmRows * kLstmH) * sizeof(float);
+    ((size_t)kLstmSmemJ * kLstmH + kG4 * kLstmRows + 4 * kLstmRows * kLstmH + kLstmBwdPre * kLstmRows * kLstmH) * sizeof(float);
 
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, const float* __restrict__ cst,
@@ -291,9 +291,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
     extern __shared__ __align__(16) float lstm_smem[];
     float* Wh = lstm_smem;                          // [4][64][128] W_hh rows 128q + jj, jj < 64
     float* dgs = Wh + kLstmSmemJ * kLstmH;          // [512][8]    dG of this step, j-major
-    float* dh = dgs + kG4 * kLstmRows;              // [8][128]
-    float* dc = dh + kLstmRows * kLstmH;            // [8][128]
-    float* part = dc + kLstmRows * kLstmH;          // [4][8][128]
+    float* part = dgs + kG4 * kLstmRows;            // [4][8][128]   (dL/dh and dL/dc of a (row, unit) pair live in its thread's registers)
     float* pre = part + 4 * kLstmRows * kLstmH;     // [6][8][128] next step's operands of the element-wise part
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kLstmRows;
