@@ -889,10 +889,15 @@ __global__ void split_h_kernel(const float* __restrict__ x, int ld_in, size_t ro
         hi[o] = h;
         lo[o] = __floats2half2_rn(fmaf(v0, 2048.f, -2048.f * hf.x), fmaf(v1, 2048.f, -2048.f * hf.y));
     };
-    if (rows == 1) {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)ldp; i += (size_t)gridDim.x * blockDim.x) {
-            const int c = (int)i * 2;
-            emit(i, c < cols ? __ldg(x + c) : 0.f, c + 1 < cols ? __ldg(x + c + 1) : 0.f);
+    if (rows == 1 || ldp < 32) {
+        // one long row, or rows narrower than a warp (the 17-wide head gradient: a warp per row left half the lanes idle and
+        // one 64-byte store per warp and trip): one thread per output pair, consecutive threads consecutive pairs
+        const size_t total = rows * (size_t)ldp;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = i / (size_t)ldp;
+            const int c = (int)(i - r * (size_t)ldp) * 2;
+            const float* xr = x + r * ld_in;
+            emit(i, c < cols ? __ldg(xr + c) : 0.f, c + 1 < cols ? __ldg(xr + c + 1) : 0.f);
         }
         return;
     }
@@ -912,7 +917,7 @@ int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out,
     if (rows == 0 || ld_out == 0) return FI_OK;
     if (ld_out & 1) return set_error(FI_ERR_ARG, "split_h: ld_out must be even");
     const size_t total = rows * (size_t)(ld_out / 2);
-    size_t blocks = rows == 1 ? (total + 255) / 256 : (rows + 7) / 8;
+    size_t blocks = (rows == 1 || ld_out / 2 < 32) ? (total + 255) / 256 : (rows + 7) / 8;
     if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
     LaunchScope ls("split_h_kernel", st, 4.0 * (double)rows * cols + 4.0 * (double)rows * ld_out, kWorkBytes);
     split_h_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, ld_out, static_cast<__half2*>(hi), static_cast<__half2*>(lo), hs,
