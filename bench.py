@@ -231,7 +231,7 @@ def bind_to_gpu_cpus(torch, local: int):
         before = os.sched_getaffinity(0)
         pynvml.nvmlDeviceSetCpuAffinity(h)
         after = os.sched_getaffinity(0)
-        if not after:
+        if len(after) < min(4, len(before)):   # a binding that leaves no room for the rank's actor threads is worse than none
             os.sched_setaffinity(0, before)
             return None
         return {"cpus": len(after), "of": len(before)}
