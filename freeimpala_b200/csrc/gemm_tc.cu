@@ -229,6 +229,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    // Programmatic dependent launch (launch_variant sets the attribute): everything above -- barrier initialisation, the TMEM
+    // allocation, the cluster handshake -- touches no global memory and may run while the previous kernel of the stream is
+    // still draining its last tiles; from here on this grid reads and writes what that kernel produced, so it waits for it
+    // (completion and visibility of all its memory operations). Then it lets ITS successor start the same way: the
+    // successor's CTAs become resident as this grid's CTAs exit and wait at this point themselves. Without the launch
+    // attribute both instructions do nothing.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // TMEM columns of chunk buffer b: main at [2b*BN, 2b*BN + BN), corr at [2b*BN + BN, 2b*BN + 2BN)
 
     if (warp == 0) {
@@ -1273,24 +1281,32 @@ static int launch_variant(const CUtensorMap* maps, const TcShape& sh, const TcEp
                                             : (narrow ? "gemm_tc_kernel<f16x3,TN,head>" : sh.n < 256 ? "gemm_tc_kernel<f16x3,TN,n162>" : "gemm_tc_kernel<f16x3,TN>")))
                           : (!B_MN ? "gemm_tc_kernel<NT>" : (!A_MN ? "gemm_tc_kernel<NN>" : "gemm_tc_kernel<TN>"));
     LaunchScope ls(label, st, 2.0 * (double)sh.m * sh.n * sh.k, kWorkFlops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     if constexpr (PAIR) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(Cfg::kThreads);
-        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;  // the two CTAs of a cluster land on one SM pair
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
-    } else {
-        gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3],
-                                                                                           maps[4], maps[5], sh, ep);
+        attr[na].id = cudaLaunchAttributeClusterDimension;  // the two CTAs of a cluster land on one SM pair
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        na++;
     }
+    // FI_PDL=0: plain stream serialisation (the kernel's griddepcontrol instructions are then no-ops)
+    static const bool pdl = [] { const char* e = getenv("FI_PDL"); return !(e && e[0] == '0'); }();
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)na;
+    const cudaError_t le =
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, PAIR, H, W16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], sh, ep);
+    if (le != cudaSuccess) return set_error(FI_ERR_CUDA, "launch of %s failed: %s", label, cudaGetErrorString(le));
     return ls.done();
 }
 
