@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -206,6 +207,33 @@ constexpr int kXPerRec = 64;
 constexpr int kHid = 512;                    // trunk width (reference main.cpp:17-21)
 constexpr int kHead = kNumActions + 1;       // fused policy/value head rows
 constexpr int kLstmH = 128;                  // reference main.cpp:16
+
+// ---- programmatic dependent launch -------------------------------------------------------------------------------
+// A kernel launched with launch_pdl may become resident while the previous kernel of the stream is still draining; it must
+// call pdl_wait() before it reads or writes global memory (the wait returns when that kernel has completed and its memory
+// operations are visible). Takes the launch latency of the short kernels between the GEMMs off the step's critical path.
+// FI_PDL=0: plain stream serialisation (pdl_wait is then a no-op).
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("FI_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 #ifdef __CUDACC__
 // ---- streaming 16-byte global accesses (no L1 allocation: every byte is touched once) ------

@@ -371,6 +371,7 @@ int launch_colsum2(const float* x, const float* x2, int ldx, int m, int n, float
 // Zero up to two small device buffers (word counts) with one tiny kernel: a cudaMemsetAsync may go through a copy engine,
 // and the learner step keeps its stream free of copy-engine hand-overs (see OptExtras in adam.cu).
 __global__ void zero_words_kernel(uint32_t* a, int na, uint32_t* b, int nb) {
+    pdl_wait();
     for (int i = threadIdx.x; i < na; i += blockDim.x) a[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) b[i] = 0u;
 }
@@ -386,8 +387,8 @@ int launch_copy_words(float* dst, const float* src, int n, cudaStream_t st) {
 int launch_zero2(void* a, size_t a_bytes, void* b, size_t b_bytes, cudaStream_t st) {
     if ((a_bytes | b_bytes) & 3) return set_error(FI_ERR_ARG, "launch_zero2: sizes must be multiples of 4");
     LaunchScope ls("zero_words_kernel", st, (double)(a_bytes + b_bytes), kWorkBytes);
-    zero_words_kernel<<<1, 128, 0, st>>>(static_cast<uint32_t*>(a), (int)(a ? a_bytes / 4 : 0), static_cast<uint32_t*>(b),
-                                         (int)(b ? b_bytes / 4 : 0));
+    launch_pdl(zero_words_kernel, dim3(1), dim3(128), 0, st, static_cast<uint32_t*>(a), (int)(a ? a_bytes / 4 : 0), static_cast<uint32_t*>(b),
+               (int)(b ? b_bytes / 4 : 0));
     return ls.done();
 }
 

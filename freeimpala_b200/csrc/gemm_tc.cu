@@ -882,6 +882,7 @@ int launch_amax(const float* x, int ld_in, size_t rows, int cols, HScale* hs, cu
 // columns [cols, ld_out) zero-filled. Two elements per thread (one 4-byte store per array). Traffic 4 + 4 B per element.
 __global__ void split_h_kernel(const float* __restrict__ x, int ld_in, size_t rows, int cols, int ld_out, __half2* __restrict__ hi,
                                __half2* __restrict__ lo, HScale* hs, int write_scale) {
+    pdl_wait();
     const float scale = hscale_from_bound(hs->amax);
     if (write_scale && blockIdx.x == 0 && threadIdx.x == 0) {
         hs->scale = scale;
@@ -928,8 +929,8 @@ int launch_split_h(const float* x, int ld_in, size_t rows, int cols, int ld_out,
     size_t blocks = (rows == 1 || ld_out / 2 < 32) ? (total + 255) / 256 : (rows + 7) / 8;
     if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
     LaunchScope ls("split_h_kernel", st, 4.0 * (double)rows * cols + 4.0 * (double)rows * ld_out, kWorkBytes);
-    split_h_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld_in, rows, cols, ld_out, static_cast<__half2*>(hi), static_cast<__half2*>(lo), hs,
-                                                     write_scale);
+    launch_pdl(split_h_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, ld_in, rows, cols, ld_out, static_cast<__half2*>(hi),
+               static_cast<__half2*>(lo), hs, write_scale);
     return ls.done();
 }
 

@@ -12,6 +12,7 @@ namespace fi {
 
 __global__ void __launch_bounds__(256)
 grad_colsum_partial_kernel(const GradSegTable t) {
+    pdl_wait();
     // blocks [first_block1[z], first_block1[z+1]) belong to column-sum segment z; block = rows [r0, r1) x 32 columns; 8 row-lanes x
     // 32 column-lanes
     int z = 0;
@@ -38,6 +39,7 @@ grad_colsum_partial_kernel(const GradSegTable t) {
 
 __global__ void __launch_bounds__(256)
 grad_finalize_kernel(const GradSegTable t) {
+    pdl_wait();
     // blocks [first_block[i], first_block[i+1]) belong to segment i
     int i = 0;
     while (i + 1 < t.count && (int)blockIdx.x >= t.first_block[i + 1]) i++;
@@ -122,11 +124,11 @@ int launch_grad_finalize(GradSegTable* t, cudaStream_t st) {
     t->first_block1[t->num_colsum] = blocks1;
     if (t->num_colsum > 0) {
         LaunchScope l1("grad_colsum_partial_kernel", st, bytes1, kWorkBytes);
-        grad_colsum_partial_kernel<<<blocks1, 256, 0, st>>>(*t);
+        launch_pdl(grad_colsum_partial_kernel, dim3(blocks1), dim3(256), 0, st, *t);
         FI_TRY(l1.done());
     }
     LaunchScope l2("grad_finalize_kernel", st, bytes2, kWorkBytes);
-    grad_finalize_kernel<<<blocks, 256, 0, st>>>(*t);
+    launch_pdl(grad_finalize_kernel, dim3(blocks), dim3(256), 0, st, *t);
     return l2.done();
 }
 

@@ -199,6 +199,7 @@ vtrace_loss_head_kernel(const float* __restrict__ batch, int m, int t, const flo
                         float* __restrict__ dhead_lo, int ld_split, HScale* __restrict__ dhead_hs) {
     __shared__ float s_head[kLossWarps][32 * kHead];
     __shared__ float s_out[kLossWarps][2][32 * 33];
+    pdl_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int traj = blockIdx.x * kLossWarps + wib;
     if (traj >= m) return;
@@ -368,9 +369,8 @@ int launch_vtrace_loss_head(const void* batch, int m, int t, const float* head, 
     // behaviour logits, action, reward, discount (19 x 4 B) = 212 B (+ 8 B when vs / pg_adv are written)
     LaunchScope ls("vtrace_loss_head_kernel", stream,
                    (212.0 + (vs ? 4.0 : 0.0) + (pg_adv ? 4.0 : 0.0)) * (double)m * t, kWorkBytes);
-    vtrace_loss_head_kernel<<<(m + warps - 1) / warps, 32 * warps, 0, stream>>>(
-        (const float*)batch, m, t, head, ldh, rho_bar, c_bar, pg_rho_bar, lambda_, baseline_cost, entropy_cost,
-        dhead, vs, pg_adv, losses, dhead_hi, dhead_lo, ld_split, dhead_hs);
+    launch_pdl(vtrace_loss_head_kernel, dim3((m + warps - 1) / warps), dim3(32 * warps), 0, stream, (const float*)batch, m, t, head, ldh, rho_bar,
+               c_bar, pg_rho_bar, lambda_, baseline_cost, entropy_cost, dhead, vs, pg_adv, losses, dhead_hi, dhead_lo, ld_split, dhead_hs);
     return ls.done();
 }
 
