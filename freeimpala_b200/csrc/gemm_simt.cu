@@ -221,6 +221,7 @@ gemm_simt_kernel(GemmArgs g) {
 // out[i] = sum_s partial[s * stride + i], fixed order (deterministic split-K reduction).
 __global__ void reduce_splits_kernel(const float* __restrict__ partial, int splits, size_t stride, size_t n,
                                      float* __restrict__ out) {
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < splits; k++) s += __ldg(partial + (size_t)k * stride + i);
@@ -258,7 +259,7 @@ int launch_reduce_splits(const float* partial, int splits, size_t stride, size_t
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
     LaunchScope lr("reduce_splits_kernel", stream, 4.0 * (double)n * (splits + 1), kWorkBytes);
-    reduce_splits_kernel<<<blocks, 256, 0, stream>>>(partial, splits, stride, n, out);
+    launch_pdl(reduce_splits_kernel, dim3(blocks), dim3(256), 0, stream, partial, splits, stride, n, out);
     return lr.done();
 }
 
@@ -322,7 +323,7 @@ int launch_gemm_simt(int trans, int m, int n, int k, const float* a, int lda, co
         int blocks = (int)((total + 255) / 256);
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         LaunchScope lr("reduce_splits_kernel", stream, 4.0 * (double)total * (splits + 1), kWorkBytes);
-        reduce_splits_kernel<<<blocks, 256, 0, stream>>>((const float*)workspace, splits, total, total, c);
+        launch_pdl(reduce_splits_kernel, dim3(blocks), dim3(256), 0, stream, (const float*)workspace, splits, total, total, c);
         FI_TRY(lr.done());
     }
     return FI_OK;

@@ -771,6 +771,7 @@ int launch_lstm_forward_tc(float* gates, const float* whh, const float* b_hh, in
 
 // db_ih = db_hh = the clusters' partial column sums of dG, added in cluster order
 __global__ void lstm_bias_grad_kernel(const float* __restrict__ part, int nparts, float* __restrict__ g_bih, float* __restrict__ g_bhh) {
+    pdl_wait();
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= kG4) return;
     float acc = 0.f;
@@ -803,7 +804,7 @@ lstm_split_gates_kernel(const float* __restrict__ gates, int m, int t, int nblk,
 
 int launch_lstm_bias_grad(const float* part, int nparts, float* g_bih, float* g_bhh, cudaStream_t st) {
     LaunchScope ls("lstm_bias_grad_kernel", st, 4.0 * kG4 * (nparts + 2), kWorkBytes);
-    lstm_bias_grad_kernel<<<2, 256, 0, st>>>(part, nparts, g_bih, g_bhh);
+    launch_pdl(lstm_bias_grad_kernel, dim3(2), dim3(256), 0, st, part, nparts, g_bih, g_bhh);
     return ls.done();
 }
 

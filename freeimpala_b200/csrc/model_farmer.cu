@@ -122,6 +122,7 @@ __global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restr
 // feat[b, 128 + j] = x_j (64 words of x in each of the first 8 records), target[b] = aux of record 0
 __global__ void farmer_assemble_kernel(const float* __restrict__ batch, int m, int t, float* __restrict__ feat,
                                        float* __restrict__ target) {
+    pdl_wait();
     const int b = blockIdx.x;
     const float* slot = batch + (size_t)b * t * kRecWords;
     for (int j = threadIdx.x; j < kXDim; j += blockDim.x) {
@@ -165,17 +166,21 @@ lstm_forward_kernel(float* __restrict__ gates, const float* __restrict__ whh_t, 
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(whh_t) + i);
     for (int i = tid; i < kLstmRows * kLstmH; i += kLstmThreads) { hs[i] = 0.f; cs[i] = 0.f; }
     const float2 bias = __ldg(reinterpret_cast<const float2*>(b_hh + j0));
+    float2 wreg[kLstmH - kLstmSmemK];
+#pragma unroll
+    for (int k = 0; k < kLstmH - kLstmSmemK; k++)
+        wreg[k] = __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)(kLstmSmemK + k) * kG4 + j0));
+    __syncthreads();
+    // Programmatic dependent launch: W_hh^T and b_hh were written at least two kernels back, so staging them (128 KB of
+    // shared memory + 128 registers per thread) overlaps the tail of the input projection; the gates it writes are touched
+    // only after this wait.
+    pdl_wait();
     if (hp_hs && blockIdx.x == 0 && tid == 0) {   // |h| <= 1: the fp16 pairs of h_prev use the constant scale 2^13, no max|x| pass
         hp_hs->scale = kHprevScale;
         hp_hs->inv = 1.f / kHprevScale;
         hp_hs->amax = 1.f;
         hp_hs->bound = 1.f;
     }
-    float2 wreg[kLstmH - kLstmSmemK];
-#pragma unroll
-    for (int k = 0; k < kLstmH - kLstmSmemK; k++)
-        wreg[k] = __ldg(reinterpret_cast<const float2*>(whh_t + (size_t)(kLstmSmemK + k) * kG4 + j0));
-    __syncthreads();
     unsigned long long* tr = (blockIdx.x == 0 && tid == 0) ? trace : nullptr;
     for (int s = 0; s < t; s++) {
         lstm_trace_ev(tr, s, 0);
@@ -319,12 +324,19 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    prefetch(t - 1);
+    // W_hh (a parameter: last written by the previous step's optimiser) is staged first; under a programmatic dependent
+    // launch that overlaps the tail of the dgrad product whose output (dfeat) is read only after the wait below.
     for (int i = tid; i < kLstmSmemJ * kLstmH / 4; i += kLstmThreads) {
         const int row = i / (kLstmH / 4), c4 = i % (kLstmH / 4);       // smem row = 64 * quarter + jj
         const int j = (row >> 6) * kLstmH + (row & 63);
         reinterpret_cast<float4*>(Wh)[i] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * kLstmH) + c4);
     }
+    const int q = tid >> 6, k0 = (tid & 63) * 2;
+    float2 wreg[64];
+#pragma unroll
+    for (int jj = 0; jj < 64; jj++) wreg[jj] = __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + 64 + jj) * kLstmH + k0));
+    pdl_wait();
+    prefetch(t - 1);
     // dL/dh and dL/dc of this thread's 4 (row, unit) pairs (unit tid % 128, rows 4 (tid / 128) + k) live in registers
     constexpr int kPairs = kLstmRows * kLstmH / kLstmThreads;
     float dhr[kPairs], dcr[kPairs];
@@ -334,10 +346,6 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
         dhr[k] = r < nrows ? dfeat[(size_t)(b0 + r) * ldf + u] : 0.f;
         dcr[k] = 0.f;
     }
-    const int q = tid >> 6, k0 = (tid & 63) * 2;
-    float2 wreg[64];
-#pragma unroll
-    for (int jj = 0; jj < 64; jj++) wreg[jj] = __ldg(reinterpret_cast<const float2*>(whh + (size_t)(q * kLstmH + 64 + jj) * kLstmH + k0));
     __syncthreads();
     // max |dG| (for the fp16 split that follows) and this CTA's column sums of dG (the bias gradient): thread tid always
     // meets unit tid % 128 (rows 4 (tid / 128) + k)
@@ -440,6 +448,7 @@ lstm_backward_kernel(float* __restrict__ gates, const float* __restrict__ whh, c
 // GLOBAL batch). losses[0] += sum_i loss_i / denom (double).
 __global__ void regression_loss_kernel(const float* __restrict__ y, const float* __restrict__ target, int m, int kind,
                                        double inv_denom, float* __restrict__ dy, double* __restrict__ losses, HScale* __restrict__ dy_hs) {
+    pdl_wait();
     double local = 0.0;
     float dmax = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
@@ -662,10 +671,10 @@ static int farmer_forward(fi_learner* l, FarmerWs* w, const float* params, const
         FI_TRY(ensure_dynamic_smem(fwd_attr, (const void*)lstm_forward_kernel, (int)kLstmFwdSmem));
         // training on the 3xFP16 path: h_prev leaves the kernel as the fp16 pairs the W_hh gradient product reads
         const bool hp_pairs = half_proj && w->hp_hi;
-        lstm_forward_kernel<<<(m + kLstmRows - 1) / kLstmRows, kLstmThreads, kLstmFwdSmem, st>>>(
-            w->gates, w->whh_t, params + T[3].offset, m, t, hp_pairs ? nullptr : w->hprev, w->cst, w->feat,
-            hp_pairs ? static_cast<__half*>(w->hp_hi) : nullptr, hp_pairs ? static_cast<__half*>(w->hp_lo) : nullptr,
-            hp_pairs ? w->hs + kHsHp : nullptr, lstm_trace_buffer());
+        launch_pdl(lstm_forward_kernel, dim3((m + kLstmRows - 1) / kLstmRows), dim3(kLstmThreads), kLstmFwdSmem, st, w->gates, w->whh_t,
+                   params + T[3].offset, m, t, hp_pairs ? nullptr : w->hprev, w->cst, w->feat,
+                   hp_pairs ? static_cast<__half*>(w->hp_hi) : nullptr, hp_pairs ? static_cast<__half*>(w->hp_lo) : nullptr,
+                   hp_pairs ? w->hs + kHsHp : nullptr, lstm_trace_buffer());
         FI_TRY(ls.done());
         lstm_trace_report("forward (FFMA)", lstm_trace_buffer(), t, st);
     }
@@ -710,15 +719,15 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
     float* g = p->grads;
     {
         LaunchScope ls("farmer_assemble_kernel", st, 2.0 * 4 * kXDim * (double)m, kWorkBytes);
-        farmer_assemble_kernel<<<m, 128, 0, st>>>(batch, m, t, w->feat, w->target);
+        launch_pdl(farmer_assemble_kernel, dim3(m), dim3(128), 0, st, batch, m, t, w->feat, w->target);
         FI_TRY(ls.done());
     }
     FI_TRY(farmer_forward(l, w, p->params, batch, kRecWords, m, t, st));
     FI_TRY(launch_zero2(p->d_losses, 4 * sizeof(double), nullptr, 0, st));
     {
         LaunchScope ls("regression_loss_kernel", st, 12.0 * m, kWorkBytes);
-        regression_loss_kernel<<<(m + 255) / 256, 256, 0, st>>>(w->y, w->target, m, l->cfg.loss, 1.0 / (double)global_m,
-                                                              w->dy, p->d_losses, farmer_dense_tc(l, w, m) ? w->dhs + kDhDy : nullptr);
+        launch_pdl(regression_loss_kernel, dim3((m + 255) / 256), dim3(256), 0, st, w->y, w->target, m, l->cfg.loss, 1.0 / (double)global_m,
+                   w->dy, p->d_losses, farmer_dense_tc(l, w, m) ? w->dhs + kDhDy : nullptr);
         FI_TRY(ls.done());
     }
     float* d = w->d_a;
@@ -811,9 +820,8 @@ int farmer_forward_backward(fi_learner* l, Player* p, const float* batch, int m,
         static std::atomic<uint64_t> bwd_attr{0};
         FI_TRY(ensure_dynamic_smem(bwd_attr, (const void*)lstm_backward_kernel, (int)kLstmBwdSmem));
         const int ctas = (m + kLstmRows - 1) / kLstmRows;
-        lstm_backward_kernel<<<ctas, kLstmThreads, kLstmBwdSmem, st>>>(w->gates, p->params + T[1].offset, w->cst, d, ldd, m, t,
-                                                                      farmer_use_half(l, w, rt) ? w->hs + kHsDg : nullptr, w->bias_part,
-                                                                      lstm_trace_buffer());
+        launch_pdl(lstm_backward_kernel, dim3(ctas), dim3(kLstmThreads), kLstmBwdSmem, st, w->gates, p->params + T[1].offset, w->cst, d, ldd, m,
+                   t, farmer_use_half(l, w, rt) ? w->hs + kHsDg : nullptr, w->bias_part, lstm_trace_buffer());
         FI_TRY(ls.done());
         lstm_trace_report("backward (FFMA)", lstm_trace_buffer(), t, st);
         // db_ih = db_hh = the CTAs' column sums of dG, added in CTA order
