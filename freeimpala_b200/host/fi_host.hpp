@@ -26,6 +26,7 @@ constexpr size_t ELEMENT_SIZE = FI_ELEMENT_SIZE;  // data_structures.h:35
 // data_structures.h:286-293); here the batch stays in HBM and empty() keeps its meaning (learner.h:79).
 struct DeviceBatch {
     fi_batch raw{};
+    bool failed = false;   // readBatch hit a CUDA / argument error (logged by the library): not a drain, not a spurious wake-up
     bool empty() const { return raw.num_slots == 0; }
     size_t size() const { return raw.num_slots; }
     std::vector<std::vector<char>> to_host() const {  // the reference's representation, for callers that need bytes
@@ -46,7 +47,10 @@ public:
     bool try_write(const std::vector<char>& data) { return fi_ring_try_write(ring_, data.data(), data.size()) == 1; } // :244-264
     DeviceBatch readBatch(size_t batch_size, void* stream = nullptr) {                                               // :267-300
         DeviceBatch b;
-        if (fi_ring_read_batch(ring_, batch_size, stream, &b.raw) < 0) b.raw.num_slots = 0;  // logged by the library
+        if (fi_ring_read_batch(ring_, batch_size, stream, &b.raw) < 0) {   // logged by the library
+            b.raw.num_slots = 0;
+            b.failed = true;
+        }
         return b;
     }
     void setDraining() { fi_ring_set_draining(ring_); }                                                              // :212-216
@@ -153,7 +157,8 @@ public:
         model_manager_ = std::make_shared<ModelManager>(h_, p);
         if (!m.empty()) model_manager_->loadModels(m);                         // learner.h:129-132
         for (size_t i = 0; i < p; i++) shared_buffers_.push_back(std::make_shared<SharedBuffer>(fi_learner_ring(h_, (int)i)));
-        iterations_.assign(p, 0);
+        iterations_ = std::make_unique<std::atomic<size_t>[]>(p);
+        for (size_t i = 0; i < p; i++) iterations_[i].store(0);
     }
     ~Learner() {
         stop();
@@ -182,7 +187,7 @@ public:
     std::vector<std::shared_ptr<SharedBuffer>> getSharedBuffers() { return shared_buffers_; }   // learner.h:200-202
     std::shared_ptr<ModelManager> getModelManager() { return model_manager_; }                   // learner.h:205-207
     fi_learner* handle() const { return h_; }
-    size_t iterationsDone(size_t p) const { return iterations_[p]; }
+    size_t iterationsDone(size_t p) const { return p < num_players_ ? iterations_[p].load(std::memory_order_acquire) : 0; }
     const StepMetrics& stepMetrics() const { return metrics_; }   // model updates / host time inside trainModel (stand-alone counters)
     // Losses of player p's optimiser step `step` (1-based, one of the last 8): {total, pg, baseline, entropy} for V-trace,
     // {loss,0,0,0} for the regression step. Waits only for that step's read-back (no counterpart in the reference, whose
@@ -190,18 +195,19 @@ public:
     bool lossesAt(size_t p, uint64_t step, float out[4]) const { return fi_learner_losses_at(h_, (int)p, step, out) == FI_OK; }
 
 private:
-    void trainModel(size_t p, const DeviceBatch& batch) {                      // learner.h:32-49
+    bool trainModel(size_t p, const DeviceBatch& batch) {                      // learner.h:32-49 (void there: no error path)
         FI_HOST_TRAINING_TIMER();                                              // learner.h:33-34
         const auto t0 = std::chrono::steady_clock::now();
         // forward, loss, backward, (all-reduce), Adam and the publication of version + 1, all enqueued on the player's stream
         if (fi_learner_step(h_, (int)p, &batch.raw) != FI_OK) {                // logged by the library; reference style: no throw
             should_stop_.store(true);
-            return;
+            return false;
         }
         metrics_.training_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                                            std::chrono::steady_clock::now() - t0).count());
         metrics_.model_updates.fetch_add(1);
         FI_HOST_RECORD_MODEL_UPDATE();                                         // learner.h:47-48
+        return true;
     }
     void checkpointModel(size_t p, uint64_t it) {                              // learner.h:52-69
         std::lock_guard<std::mutex> lock(checkpoint_mutex_);
@@ -215,11 +221,14 @@ private:
         while (!should_stop_.load() && it < total_iterations_) {
             DeviceBatch batch = shared_buffers_[p]->readBatch(batch_size_, stream);
             if (batch.empty()) {
+                // a failed read (sticky H2D failure, bad batch size) would fail again at once: stop instead of spinning;
+                // a drained or spurious empty batch loops as in the reference (learner.h:79-84)
+                if (batch.failed) should_stop_.store(true);
                 if (should_stop_.load()) break;
                 continue;
             }
-            trainModel(p, batch);
-            iterations_[p] = ++it;
+            if (!trainModel(p, batch)) break;   // a failed step is not counted as an iteration
+            iterations_[p].store(++it, std::memory_order_release);
             if (checkpoint_frequency_ > 0 && it % checkpoint_frequency_ == 0 && !checkpoint_location_.empty()) checkpointModel(p, it);
         }
     }
@@ -231,7 +240,7 @@ private:
     std::shared_ptr<ModelManager> model_manager_;
     std::vector<std::shared_ptr<SharedBuffer>> shared_buffers_;
     std::vector<std::thread> worker_threads_, checkpoint_threads_;
-    std::vector<size_t> iterations_;
+    std::unique_ptr<std::atomic<size_t>[]> iterations_;   // per player; read by other threads (iterationsDone)
     std::atomic<bool> should_stop_{false}, stopped_{false};
     std::mutex checkpoint_mutex_;
     StepMetrics metrics_;

@@ -152,6 +152,11 @@ def main():
             res["gather"].append(sweep_gather(M, T, peak))
             res["vtrace"].append(sweep_vtrace(M, T, peak))
             torch.cuda.empty_cache()
+    # beyond configs[4]'s grid: the sizes at which the scan's working set leaves L2 and the launch ramp stops mattering
+    # ("quote the size at which >= 70 % is reached")
+    for M, T in [(8192, 400), (16384, 400)]:
+        res["vtrace"].append(sweep_vtrace(M, T, peak))
+        torch.cuda.empty_cache()
     for n in [1142801, 1514497, 8 * 2 ** 20, 64 * 2 ** 20, 256 * 2 ** 20]:
         res["adam"].append(sweep_adam(n, peak))
         torch.cuda.empty_cache()
