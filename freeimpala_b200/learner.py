@@ -158,14 +158,14 @@ class Learner:
         it = 0
         stream = self._lib.fi_learner_stream(self._h, p)
         while not self.should_stop.is_set() and it < self.total_iterations:
-            batch = self.shared_buffers[p].readBatch(self.batch_size, stream)
-            if batch.empty():
-                if self.should_stop.is_set():
-                    break
-                continue
             try:
+                batch = self.shared_buffers[p].readBatch(self.batch_size, stream)
+                if batch.empty():
+                    if self.should_stop.is_set():
+                        break
+                    continue
                 self.trainModel(p, batch)
-            except _lib.FiError as e:  # reference style: log and stop
+            except _lib.FiError as e:  # reference style: log and stop; a failed read would fail again at once
                 self.errors.append(str(e))
                 self.should_stop.set()
                 break
