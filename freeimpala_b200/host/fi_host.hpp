@@ -188,6 +188,7 @@ public:
     std::shared_ptr<ModelManager> getModelManager() { return model_manager_; }                   // learner.h:205-207
     fi_learner* handle() const { return h_; }
     size_t iterationsDone(size_t p) const { return p < num_players_ ? iterations_[p].load(std::memory_order_acquire) : 0; }
+    bool failed() const { return failed_.load(); }   // a worker stopped on a failed readBatch / step (fi_last_error was logged)
     const StepMetrics& stepMetrics() const { return metrics_; }   // model updates / host time inside trainModel (stand-alone counters)
     // Losses of player p's optimiser step `step` (1-based, one of the last 8): {total, pg, baseline, entropy} for V-trace,
     // {loss,0,0,0} for the regression step. Waits only for that step's read-back (no counterpart in the reference, whose
@@ -200,6 +201,7 @@ private:
         const auto t0 = std::chrono::steady_clock::now();
         // forward, loss, backward, (all-reduce), Adam and the publication of version + 1, all enqueued on the player's stream
         if (fi_learner_step(h_, (int)p, &batch.raw) != FI_OK) {                // logged by the library; reference style: no throw
+            failed_.store(true);
             should_stop_.store(true);
             return false;
         }
@@ -223,7 +225,7 @@ private:
             if (batch.empty()) {
                 // a failed read (sticky H2D failure, bad batch size) would fail again at once: stop instead of spinning;
                 // a drained or spurious empty batch loops as in the reference (learner.h:79-84)
-                if (batch.failed) should_stop_.store(true);
+                if (batch.failed) { failed_.store(true); should_stop_.store(true); }
                 if (should_stop_.load()) break;
                 continue;
             }
@@ -241,7 +243,7 @@ private:
     std::vector<std::shared_ptr<SharedBuffer>> shared_buffers_;
     std::vector<std::thread> worker_threads_, checkpoint_threads_;
     std::unique_ptr<std::atomic<size_t>[]> iterations_;   // per player; read by other threads (iterationsDone)
-    std::atomic<bool> should_stop_{false}, stopped_{false};
+    std::atomic<bool> should_stop_{false}, stopped_{false}, failed_{false};
     std::mutex checkpoint_mutex_;
     StepMetrics metrics_;
 };

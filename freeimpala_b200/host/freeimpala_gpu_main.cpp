@@ -112,7 +112,7 @@ int main(int argc, char** argv) {
         // at this point, so let the workers finish them (bounded wait) to make the run deterministic.
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(120);
         auto done = [&] { size_t u = 0; for (size_t p = 0; p < P.players; p++) u += learner.iterationsDone(p); return u; };
-        while (done() < learner_iterations * P.players && std::chrono::steady_clock::now() < deadline)
+        while (done() < learner_iterations * P.players && !learner.failed() && std::chrono::steady_clock::now() < deadline)
             std::this_thread::sleep_for(std::chrono::microseconds(200));
         learner.stop();
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

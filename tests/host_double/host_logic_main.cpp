@@ -112,8 +112,8 @@ static void scenario_step_failure() {
     const long reads_later = fi_double_read_calls();
     learner.stop();
     fi_double_fail_step_after(-1);
-    printf("\"step_failure\": {\"iterations\": %zu, \"updates_counted\": %llu, \"read_calls_while_idle\": %ld}", learner.iterationsDone(0),
-           (unsigned long long)learner.stepMetrics().model_updates.load(), reads_later - reads);
+    printf("\"step_failure\": {\"iterations\": %zu, \"updates_counted\": %llu, \"read_calls_while_idle\": %ld, \"failed\": %s}", learner.iterationsDone(0),
+           (unsigned long long)learner.stepMetrics().model_updates.load(), reads_later - reads, learner.failed() ? "true" : "false");
 }
 
 // (4) readBatch itself fails (a sticky host-to-device failure in the product): the worker stops instead of retrying for ever.

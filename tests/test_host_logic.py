@@ -50,7 +50,7 @@ def test_stop_drains_blocked_workers(report):
 def test_failing_step_stops_the_worker(report):
     s = report["step_failure"]
     assert s["iterations"] == 2 and s["updates_counted"] == 2        # the failed step is not counted
-    assert s["read_calls_while_idle"] == 0                            # and the worker has left its loop
+    assert s["read_calls_while_idle"] == 0 and s["failed"]           # and the worker has left its loop; Learner::failed() says why
 
 
 def test_failing_read_stops_the_worker_instead_of_spinning(report):
