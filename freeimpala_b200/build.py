@@ -21,6 +21,10 @@ LIB = os.path.join(OUT_DIR, "libfreeimpala_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
+# diagnostics build: the clock64 trace hooks of the tcgen05 GEMM and the recurrent kernels (FI_TC_TRACE / FI_LSTM_TRACE) are compiled
+# in only on request -- `FI_TRACE_BUILD=1 python -m freeimpala_b200.build --force` (csrc/fi_internal.cuh says why)
+if os.environ.get("FI_TRACE_BUILD", "0") == "1":
+    NVCC_FLAGS.append("-DFI_TRACE_BUILD=1")
 
 
 def _nvcc() -> str:

@@ -142,6 +142,28 @@ int launch_lstm_backward_tc(float* gates, const float* whh, const float* cst, co
                             float* bias_part, float* g_bih, float* g_bhh, cudaStream_t st);
 // db_ih = db_hh = sum over the BPTT kernel's CTAs (or clusters) of their column sums of dG, in index order
 int launch_lstm_bias_grad(const float* part, int nparts, float* g_bih, float* g_bhh, cudaStream_t st);
+// Trace hooks (the clock64 stamps behind FI_TC_TRACE / FI_LSTM_TRACE) are COMPILED OUT of the product build: a disabled hook
+// is still a handful of predicated instructions per event, and in the tcgen05 GEMM those were 8.9 % of all warp instructions
+// executed (ncu source page of the final round-2 build, profiles/r2_gemm.md). `FI_TRACE_BUILD=1 python -m freeimpala_b200.build
+// --force` compiles them in for tools/gemm_trace.py and the LSTM phase trace; the environment switches then work as before.
+#ifndef FI_TRACE_BUILD
+#define FI_TRACE_BUILD 0
+#endif
+// true when this library carries the trace hooks; the host side warns once when a trace is requested without them
+inline bool trace_hooks_built(const char* what) {
+#if FI_TRACE_BUILD
+    (void)what;
+    return true;
+#else
+    static bool warned = false;
+    if (!warned) {
+        warned = true;
+        fprintf(stderr, "[freeimpala_b200] %s is set but this library was built without the trace hooks: rebuild with "
+                        "FI_TRACE_BUILD=1 python -m freeimpala_b200.build --force\n", what);
+    }
+    return false;
+#endif
+}
 // FI_LSTM_TRACE=1 (diagnostics): a device buffer of [128 steps][12 points] clock64 stamps written by the first thread (points
 // 0..7) and a second role (8..11) of CTA 0 of a recurrent kernel; the report prints median clocks between consecutive points
 unsigned long long* lstm_trace_buffer();

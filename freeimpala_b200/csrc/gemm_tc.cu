@@ -99,12 +99,17 @@ constexpr int kTraceCtas = 4, kTraceRoles = 3, kTraceCap = 4096;
 struct TraceLog {
     unsigned long long* p = nullptr;
     int n = 0;
+#if FI_TRACE_BUILD
     __device__ __forceinline__ void init(unsigned long long* base, int role) {
         if (base && blockIdx.x < kTraceCtas) p = base + ((size_t)blockIdx.x * kTraceRoles + role) * kTraceCap;
     }
     __device__ __forceinline__ void ev(unsigned tag) {
         if (p && n < kTraceCap) p[n++] = ((unsigned long long)clock64() << 8) | tag;
     }
+#else   // product build: no hook costs an instruction (fi_internal.cuh)
+    __device__ __forceinline__ void init(unsigned long long*, int) {}
+    __device__ __forceinline__ void ev(unsigned) {}
+#endif
 };
 
 // column sums of a 32 x 32 block held one row per lane (x[i] = column i of this lane's row) by recursive halving: after the
@@ -1219,7 +1224,7 @@ static unsigned long long* tc_trace_buffer(int trans, int /*m*/, int n, int k) {
         if (e) r.on = sscanf(e, "%d,%d,%d,%d", &r.trans, &r.n, &r.k, &r.kmax) >= 1;
         return r;
     }();
-    if (!f.on || trans != f.trans || n < f.n || k < f.k || k > f.kmax) return nullptr;
+    if (!f.on || !trace_hooks_built("FI_TC_TRACE") || trans != f.trans || n < f.n || k < f.k || k > f.kmax) return nullptr;
     const size_t bytes = (size_t)kTraceCtas * kTraceRoles * kTraceCap * sizeof(unsigned long long);
     if (!g_tc_trace && cudaMalloc((void**)&g_tc_trace, bytes) != cudaSuccess) return nullptr;
     cudaMemset(g_tc_trace, 0, bytes);   // legacy-stream memset: diagnostics only

@@ -113,7 +113,11 @@ __device__ float cta_weight_scale(const float* __restrict__ whh, int rank, float
 // (points 8..11); the host prints the median phase lengths after each launch (diagnostics; forces a stream sync).
 constexpr int kTracePoints = 12, kTraceSteps = 128;
 __device__ __forceinline__ void trace_ev(unsigned long long* tr, int s, int point) {
+#if FI_TRACE_BUILD
     if (tr && s < kTraceSteps) tr[s * kTracePoints + point] = clock64();
+#else
+    (void)tr; (void)s; (void)point;
+#endif
 }
 
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B (K-major tiles)
@@ -673,7 +677,7 @@ unsigned long long* lstm_trace_buffer() {
     static unsigned long long* buf = [] {
         unsigned long long* p = nullptr;
         const char* e = getenv("FI_LSTM_TRACE");
-        if (e && e[0] == '1' && cudaMalloc((void**)&p, sizeof(unsigned long long) * kTracePoints * kTraceSteps) != cudaSuccess) p = nullptr;
+        if (e && e[0] == '1' && trace_hooks_built("FI_LSTM_TRACE") && cudaMalloc((void**)&p, sizeof(unsigned long long) * kTracePoints * kTraceSteps) != cudaSuccess) p = nullptr;
         return p;
     }();
     return buf;

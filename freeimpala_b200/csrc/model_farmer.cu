@@ -107,7 +107,11 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 }
 
 __device__ __forceinline__ void lstm_trace_ev(unsigned long long* tr, int s, int point) {   // FI_LSTM_TRACE (fi_internal.cuh)
+#if FI_TRACE_BUILD
     if (tr && s < 128) tr[s * 12 + point] = clock64();
+#else
+    (void)tr; (void)s; (void)point;
+#endif
 }
 
 // out[k][j] = in[j][k] for the [512,128] recurrent weight

@@ -1,4 +1,5 @@
-"""Pipeline trace of the tcgen05 GEMM (GPU): runs a few learner steps with FI_TC_TRACE set and prints, per role of CTA 0..3,
+"""(Needs a library with the trace hooks compiled in: FI_TRACE_BUILD=1 python -m freeimpala_b200.build --force.)
+Pipeline trace of the tcgen05 GEMM (GPU): runs a few learner steps with FI_TC_TRACE set and prints, per role of CTA 0..3,
 how long each pipeline event takes (median / p90 clocks between consecutive events of that role).
 
     FI_TC_TRACE=0,512,512 python tools/gemm_trace.py     # NT products with n >= 512 and k >= 512 (forward, big layers)
