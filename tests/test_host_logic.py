@@ -82,3 +82,40 @@ def test_host_logic_is_clean_under_thread_sanitizer(tmp_path):
         pytest.skip(out.stderr[-200:])
     assert out.returncode == 0 and "WARNING: ThreadSanitizer" not in out.stderr, out.stderr[-2000:]
     assert json.loads(out.stdout)["run"]["fifo"]
+
+
+REF = "/root/reference"
+SPDLOG = "/opt/prime-rl/.venv/lib/python3.12/site-packages/flashinfer/data/spdlog/include"
+
+
+@pytest.mark.parametrize("tsan", [False, True])
+def test_reference_agent_runs_against_the_shim_on_the_cpu(tmp_path, tsan):
+    """The reference's UNMODIFIED include/freeimpala/agent.h (2 players x 3 Agent threads, its own MetricsTracker) driven
+    against fi_host.hpp exactly as in tests/test_gpu_host.py, but linked with the test double instead of the product
+    library: the plumbing the reference's actors rely on (SharedBuffer::write from transfer threads created per iteration,
+    ModelManager polling, agent.h:78-165) is exercised without a GPU, once more under ThreadSanitizer. Needs the reference
+    tree (present in the build container, absent on the GPU box)."""
+    root = os.path.dirname(HERE)
+    if not os.path.exists(os.path.join(REF, "include", "freeimpala", "agent.h")) or not os.path.isdir(SPDLOG):
+        pytest.skip("the reference tree / spdlog headers are not present here")
+    exe = tmp_path / "agent_dropin_double"
+    shim = os.path.join(root, "oracle", "ref_shim")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-w", "-o", str(exe), os.path.join(shim, "dropin_main.cpp"),
+           os.path.join(HERE, "host_double", "fi_double.cpp"),
+           f'-DFI_REF_DATA_STRUCTURES_H="{REF}/include/freeimpala/data_structures.h"', f'-DFI_REF_AGENT_H="{REF}/include/freeimpala/agent.h"',
+           "-I" + os.path.join(shim, "dropin"), "-I" + os.path.join(REF, "include"), "-I" + SPDLOG,
+           "-I" + os.path.join(root, "freeimpala_b200", "host"), "-I" + os.path.join(root, "include")]
+    if tsan:
+        cmd.insert(1, "-fsanitize=thread")
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    if build.returncode != 0 and tsan:
+        pytest.skip("libtsan is not available to this g++: " + build.stderr[-200:])
+    assert build.returncode == 0, build.stderr[-3000:]
+    out = subprocess.run([str(exe), "2", "3"], capture_output=True, text=True, timeout=300)
+    if tsan and "FATAL: ThreadSanitizer" in out.stderr:
+        pytest.skip(out.stderr[-200:])
+    assert out.returncode == 0 and "DROPIN_OK" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
+    assert "learner model updates 12" in out.stdout      # 2 players x (3 agents x 8 iterations / batch 4) updates
+    if tsan:
+        ours = [b for b in out.stderr.split("WARNING: ThreadSanitizer")[1:] if "fi_host.hpp" in b or "fi_double.cpp" in b]
+        assert not ours, ours[0][:3000]
